@@ -1,0 +1,264 @@
+// C-ABI of libhsmm_b200.so (see include/hsmm_b200.h).  Argument checking, variant dispatch, error
+// reporting.  No allocation, no synchronisation: every call enqueues kernels on the caller's stream.
+#include <stdarg.h>
+#include <string.h>
+
+#include "../../include/hsmm_b200.h"
+#include "hsmm_common.cuh"
+
+namespace hsmm {
+
+static thread_local char g_err[512] = "";
+std::atomic<uint64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int check_launch(const char* what) {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("%s: %s", what, cudaGetErrorString(e));
+        return HSMM_ERR_CUDA;
+    }
+    return HSMM_OK;
+}
+
+static int num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+            n = 148;
+    }
+    return n;
+}
+
+// implemented in the kernel translation units
+bool dp_reg_supported(int C, int L, int mode);
+const char* dp_reg_name(int C, int L, int mode);
+int dp_reg_launch(DpParams p, int mode, cudaStream_t st);
+int launch_emission(const float*, const float*, const float*, const float*, float, const float*, const int32_t*, int, int, int,
+                    int, int, float*, float*, double*, cudaStream_t);
+int launch_weighted_sums(const float*, const float*, int, const int32_t*, int, int, int, int, float*, float*, int, cudaStream_t);
+int launch_moments(const float*, const int32_t*, int, int, int, double*, double*, int, cudaStream_t);
+int launch_onehot(const int32_t*, const int32_t*, int, int, int, int, float*, int, cudaStream_t);
+int launch_gold(const float*, int, const float*, const float*, const float*, const float*, const double*, const int32_t*,
+                const int32_t*, const float*, int, int, int, int, double*, float*, float*, float*, float*, cudaStream_t);
+
+static int check_dims(const char* fn, int B, int Tmax, int C, int K, int ldc) {
+    if (B <= 0 || Tmax <= 0 || C <= 0) {
+        set_error("%s: empty batch (B=%d Tmax=%d C=%d)", fn, B, Tmax, C);
+        return HSMM_ERR_SHAPE;
+    }
+    if (K < 2) {
+        set_error("%s: K=%d leaves no usable segment length (need K >= 2)", fn, K);
+        return HSMM_ERR_SHAPE;
+    }
+    if (ldc < C) {
+        set_error("%s: ldc=%d < C=%d", fn, ldc, C);
+        return HSMM_ERR_SHAPE;
+    }
+    if (C > 65535 || K > 65535) {
+        set_error("%s: C or K exceeds the 16-bit back-pointer fields", fn);
+        return HSMM_ERR_SHAPE;
+    }
+    return HSMM_OK;
+}
+
+struct Saved {  // layout of the `saved` buffer of hsmm_logz_forward
+    float* fbeta;
+    float* fgamma;
+    float* logz2;
+};
+static size_t plane_elems(int B, int Tmax, int C) { return (size_t)B * (Tmax + 1) * (size_t)((C + 3) / 4 * 4); }
+static Saved carve(void* saved, int B, int Tmax, int C) {
+    Saved s;
+    const size_t n = plane_elems(B, Tmax, C);
+    s.fbeta = reinterpret_cast<float*>(saved);
+    s.fgamma = s.fbeta + n;
+    s.logz2 = s.fgamma + n;
+    return s;
+}
+
+}  // namespace hsmm
+
+using namespace hsmm;
+
+extern "C" {
+
+int hsmm_version(void) { return 100; }
+const char* hsmm_last_error(void) { return g_err; }
+uint64_t hsmm_launch_count(void) { return g_launches.load(); }
+
+const char* hsmm_dp_variant(int C, int K, int mode) {
+    const int L = K - 1;
+    if (dp_reg_supported(C, L, mode)) return dp_reg_name(C, L, mode);
+    return "unsupported";
+}
+
+size_t hsmm_viterbi_workspace_bytes(int B, int Tmax, int C, int K) {
+    (void)K;
+    return plane_elems(B, Tmax, C) * sizeof(uint32_t);
+}
+
+size_t hsmm_logz_saved_bytes(int B, int Tmax, int C, int K) {
+    (void)K;
+    return (2 * plane_elems(B, Tmax, C) + (size_t)B + 4) * sizeof(float);
+}
+
+int hsmm_emission(const float* X, const float* w, const float* bias, const float* inv_var, float row_const,
+                  const float* penalty, const int32_t* lengths, int B, int Tmax, int D, int C, int ldc, float* em,
+                  float* rowterm, double* offset, void* stream) {
+    if (!X || !w || !bias || !inv_var || !lengths || !em || !rowterm || !offset) {
+        set_error("hsmm_emission: null pointer");
+        return HSMM_ERR_ARG;
+    }
+    if (B <= 0 || Tmax <= 0 || D <= 0 || C <= 0 || ldc < C) {
+        set_error("hsmm_emission: bad shape B=%d Tmax=%d D=%d C=%d ldc=%d", B, Tmax, D, C, ldc);
+        return HSMM_ERR_SHAPE;
+    }
+    if (B > 65535) {
+        set_error("hsmm_emission: B=%d exceeds grid.y; split the batch", B);
+        return HSMM_ERR_SHAPE;
+    }
+    return launch_emission(X, w, bias, inv_var, row_const, penalty, lengths, B, Tmax, D, C, ldc, em, rowterm, offset,
+                           (cudaStream_t)stream);
+}
+
+int hsmm_viterbi(const float* em, int ldc, const float* init, const float* trans, const float* lenp, const float* end,
+                 const double* offset, const int32_t* lengths, const int32_t* order, const int32_t* class_ids, int B,
+                 int Tmax, int C, int K, int64_t* out_spans, int64_t* out_labels, double* out_score, void* workspace,
+                 void* stream) {
+    if (!em || !init || !trans || !lenp || !lengths || !out_spans || !workspace) {
+        set_error("hsmm_viterbi: null pointer");
+        return HSMM_ERR_ARG;
+    }
+    int rc = check_dims("hsmm_viterbi", B, Tmax, C, K, ldc);
+    if (rc) return rc;
+    if (ldc != (C + 3) / 4 * 4) {
+        set_error("hsmm_viterbi: ldc must be C rounded up to a multiple of 4 (got %d for C=%d)", ldc, C);
+        return HSMM_ERR_SHAPE;
+    }
+    DpParams p;
+    memset(&p, 0, sizeof(p));
+    p.em = em; p.init = init; p.trans = trans; p.lenp = lenp; p.end = end; p.offset = offset;
+    p.lengths = lengths; p.order = order; p.B = B; p.Tmax = Tmax; p.C = C; p.L = K - 1; p.ldc = ldc;
+    p.bp = reinterpret_cast<uint32_t*>(workspace); p.class_ids = class_ids; p.spans = out_spans; p.labels = out_labels;
+    p.score = out_score;
+    if (dp_reg_supported(C, p.L, 0)) return dp_reg_launch(p, 0, (cudaStream_t)stream);
+    set_error("hsmm_viterbi: shape C=%d K=%d exceeds on-chip capacity", C, K);
+    return HSMM_ERR_SHAPE;
+}
+
+int hsmm_logz_forward(const float* em, int ldc, const float* init, const float* trans, const float* lenp, const float* end,
+                      const double* offset, const int32_t* lengths, const int32_t* order, int B, int Tmax, int C, int K,
+                      double* out_logz, void* saved, void* stream) {
+    if (!em || !init || !trans || !lenp || !lengths || !out_logz || !saved) {
+        set_error("hsmm_logz_forward: null pointer");
+        return HSMM_ERR_ARG;
+    }
+    int rc = check_dims("hsmm_logz_forward", B, Tmax, C, K, ldc);
+    if (rc) return rc;
+    if (ldc != (C + 3) / 4 * 4) {
+        set_error("hsmm_logz_forward: ldc must be C rounded up to a multiple of 4");
+        return HSMM_ERR_SHAPE;
+    }
+    DpParams p;
+    memset(&p, 0, sizeof(p));
+    p.em = em; p.init = init; p.trans = trans; p.lenp = lenp; p.end = end; p.offset = offset;
+    p.lengths = lengths; p.order = order; p.B = B; p.Tmax = Tmax; p.C = C; p.L = K - 1; p.ldc = ldc;
+    Saved s = carve(saved, B, Tmax, C);
+    p.fbeta = s.fbeta; p.fgamma = s.fgamma; p.logz2 = s.logz2; p.logz = out_logz;
+    if (!dp_reg_supported(C, p.L, 1)) {
+        set_error("hsmm_logz_forward: shape C=%d K=%d not supported (register-resident DP only)", C, K);
+        return HSMM_ERR_SHAPE;
+    }
+    return dp_reg_launch(p, 1, (cudaStream_t)stream);
+}
+
+int hsmm_logz_backward(const float* em, int ldc, const float* init, const float* trans, const float* lenp, const float* end,
+                       const int32_t* lengths, const int32_t* order, const float* grad_logz, int B, int Tmax, int C, int K,
+                       const void* saved, float* d_init, float* d_trans, float* d_len, float* d_em, void* stream) {
+    if (!em || !init || !trans || !lenp || !lengths || !grad_logz || !saved || !d_init || !d_trans || !d_len || !d_em) {
+        set_error("hsmm_logz_backward: null pointer");
+        return HSMM_ERR_ARG;
+    }
+    int rc = check_dims("hsmm_logz_backward", B, Tmax, C, K, ldc);
+    if (rc) return rc;
+    DpParams p;
+    memset(&p, 0, sizeof(p));
+    p.em = em; p.init = init; p.trans = trans; p.lenp = lenp; p.end = end;
+    p.lengths = lengths; p.order = order; p.B = B; p.Tmax = Tmax; p.C = C; p.L = K - 1; p.ldc = ldc;
+    Saved s = carve(const_cast<void*>(saved), B, Tmax, C);
+    p.fbeta = s.fbeta; p.fgamma = s.fgamma; p.logz2 = s.logz2;
+    p.grad = grad_logz; p.d_init = d_init; p.d_trans = d_trans; p.d_len = d_len; p.d_em = d_em;
+    if (!dp_reg_supported(C, p.L, 2)) {
+        set_error("hsmm_logz_backward: shape C=%d K=%d not supported (register-resident DP only)", C, K);
+        return HSMM_ERR_SHAPE;
+    }
+    return dp_reg_launch(p, 2, (cudaStream_t)stream);
+}
+
+int hsmm_weighted_feature_sums(const float* X, const float* weights, int ldc, const int32_t* lengths, int B, int Tmax, int D,
+                               int C, float* out_wx, float* out_wsum, void* stream) {
+    if (!X || !weights || !lengths || !out_wx || !out_wsum) {
+        set_error("hsmm_weighted_feature_sums: null pointer");
+        return HSMM_ERR_ARG;
+    }
+    if (B <= 0 || Tmax <= 0 || D <= 0 || C <= 0 || ldc < C) {
+        set_error("hsmm_weighted_feature_sums: bad shape");
+        return HSMM_ERR_SHAPE;
+    }
+    return launch_weighted_sums(X, weights, ldc, lengths, B, Tmax, D, C, out_wx, out_wsum, num_sms(), (cudaStream_t)stream);
+}
+
+int hsmm_gold_score(const float* em, int ldc, const float* init, const float* trans, const float* lenp, const float* end,
+                    const double* offset, const int32_t* lengths, const int32_t* spans, const float* grad_score, int B,
+                    int Tmax, int C, int K, double* out_score, float* d_init, float* d_trans, float* d_len, float* d_em,
+                    void* stream) {
+    if (!em || !init || !trans || !lenp || !lengths || !spans || !out_score) {
+        set_error("hsmm_gold_score: null pointer");
+        return HSMM_ERR_ARG;
+    }
+    if (grad_score && (!d_init || !d_trans || !d_len || !d_em)) {
+        set_error("hsmm_gold_score: gradient requested without output buffers");
+        return HSMM_ERR_ARG;
+    }
+    int rc = check_dims("hsmm_gold_score", B, Tmax, C, K, ldc);
+    if (rc) return rc;
+    return launch_gold(em, ldc, init, trans, lenp, end, offset, lengths, spans, grad_score, B, Tmax, C, K - 1, out_score,
+                       d_init, d_trans, d_len, d_em, (cudaStream_t)stream);
+}
+
+int hsmm_feature_moments(const float* X, const int32_t* lengths, int B, int Tmax, int D, double* out_sum_x,
+                         double* out_sum_x2, void* stream) {
+    if (!X || !lengths || !out_sum_x || !out_sum_x2) {
+        set_error("hsmm_feature_moments: null pointer");
+        return HSMM_ERR_ARG;
+    }
+    if (B <= 0 || Tmax <= 0 || D <= 0) {
+        set_error("hsmm_feature_moments: bad shape");
+        return HSMM_ERR_SHAPE;
+    }
+    return launch_moments(X, lengths, B, Tmax, D, out_sum_x, out_sum_x2, num_sms(), (cudaStream_t)stream);
+}
+
+int hsmm_onehot_weights(const int32_t* labels, const int32_t* lengths, int B, int Tmax, int C, int ldc, float* weights,
+                        void* stream) {
+    if (!labels || !lengths || !weights) {
+        set_error("hsmm_onehot_weights: null pointer");
+        return HSMM_ERR_ARG;
+    }
+    if (B <= 0 || Tmax <= 0 || C <= 0 || ldc < C) {
+        set_error("hsmm_onehot_weights: bad shape");
+        return HSMM_ERR_SHAPE;
+    }
+    return launch_onehot(labels, lengths, B, Tmax, C, ldc, weights, num_sms(), (cudaStream_t)stream);
+}
+
+}  // extern "C"

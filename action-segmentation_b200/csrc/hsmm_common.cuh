@@ -1,0 +1,119 @@
+// Shared device/host helpers for the HSMM kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <atomic>
+
+namespace hsmm {
+
+constexpr float NEG = -1.0e30f;            // absorbing "minus infinity" that never produces NaN
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr double LN2 = 0.6931471805599453;
+constexpr unsigned FULL = 0xffffffffu;
+
+// ---- error plumbing (host) ----------------------------------------------------------------
+void set_error(const char* fmt, ...);
+extern std::atomic<uint64_t> g_launches;
+int check_launch(const char* what);
+
+// ---- device helpers -----------------------------------------------------------------------
+__device__ __forceinline__ float ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float lg2(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// Barrier over the `nwarps` warps that cooperate on one video.  One warp: __syncwarp.
+// Several warps: a named barrier (ids 1..15; id 0 is __syncthreads).
+__device__ __forceinline__ void group_sync(int nwarps, int bar_id) {
+    if (nwarps == 1) {
+        __syncwarp();
+    } else {
+        asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(nwarps * 32) : "memory");
+    }
+}
+
+// Combine a value across the S k-slices of a class inside one warp (lanes cl + j*CPW).
+template <int S>
+__device__ __forceinline__ float slice_max(float v) {
+#pragma unroll
+    for (int off = 32 / S; off < 32; off <<= 1) v = fmaxf(v, __shfl_xor_sync(FULL, v, off));
+    return v;
+}
+template <int S>
+__device__ __forceinline__ float slice_sum(float v) {
+#pragma unroll
+    for (int off = 32 / S; off < 32; off <<= 1) v += __shfl_xor_sync(FULL, v, off);
+    return v;
+}
+// arg-max with ties going to the smaller index
+template <int S>
+__device__ __forceinline__ void slice_argmax(float& v, int& idx) {
+#pragma unroll
+    for (int off = 32 / S; off < 32; off <<= 1) {
+        float ov = __shfl_xor_sync(FULL, v, off);
+        int oi = __shfl_xor_sync(FULL, idx, off);
+        if (ov > v || (ov == v && oi < idx)) {
+            v = ov;
+            idx = oi;
+        }
+    }
+}
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v = fmaxf(v, __shfl_xor_sync(FULL, v, off));
+    return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(FULL, v, off);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(FULL, v, off);
+    return v;
+}
+
+// ---- DP parameter block -------------------------------------------------------------------
+struct DpParams {
+    // inputs
+    const float* em;       // (B, Tmax, ldc)
+    const float* init;     // (C)
+    const float* trans;    // (C, C) [to, from]
+    const float* lenp;     // (K, C), rows 0..K-1
+    const float* end;      // (B, C) or null
+    const double* offset;  // (B) or null
+    const int32_t* lengths;
+    const int32_t* order;  // (B) or null
+    int B, Tmax, C, L, ldc;
+    int W;    // warps per video
+    int VPB;  // videos per block
+    // viterbi
+    uint32_t* bp;             // (B, Tmax+1, ldc): (k << 16) | c1
+    const int32_t* class_ids;  // (C+1) or null
+    int64_t* spans;           // (B, Tmax+1)
+    int64_t* labels;          // (B, Tmax) or null
+    double* score;            // (B) or null
+    // forward
+    float* fbeta;   // (B, Tmax+1, ldc)  beta[n], n = 0..T-1   (log2 domain)
+    float* fgamma;  // (B, Tmax+1, ldc)  gamma[n], n = 1..T    (log2 domain)
+    float* logz2;   // (B) log2-domain logZ without offset
+    double* logz;   // (B)
+    // backward
+    const float* grad;  // (B)
+    float* d_init;
+    float* d_trans;  // (C, C)
+    float* d_len;    // (K, C)
+    float* d_em;     // (B, Tmax, ldc)
+};
+
+}  // namespace hsmm

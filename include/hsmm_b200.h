@@ -1,0 +1,167 @@
+/*
+ * hsmm_b200 -- C-ABI of the B200-native HSMM hot path (libhsmm_b200.so).
+ *
+ * Drop-in boundary for the reference's `--classifier semimarkov` path
+ * (dpfried/action-segmentation).  Every entry point names the reference interface it replaces
+ * (paths relative to /root/reference/src).  The reference never calls native code of its own:
+ * the arithmetic below is what models/semimarkov/semimarkov_modules.py builds out of torch ops
+ * and hands to the un-vendored pytorch-struct (`SemiMarkovCRF`) / genbmm.  INTEGRATION.md shows
+ * the ctypes stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers owned by the caller (PyTorch), row-major, fp32 unless noted;
+ *   - `stream` is a cudaStream_t passed as void*; every call is asynchronous on that stream and
+ *     allocates nothing;
+ *   - return value 0 = ok, <0 = argument / shape / capacity / CUDA error; the message is available
+ *     from hsmm_last_error() (thread-local);
+ *   - B videos, Tmax padded frames, D feature dims, C valid classes (EOS excluded), K rows of the
+ *     length table (usable segment lengths 1..K-1, already clamped by the caller to the padded
+ *     batch length as semimarkov_modules.py:450-452 does);
+ *   - class scores use a leading dimension `ldc >= C` (multiple of 4 recommended);
+ *   - transition scores are indexed [to, from] (semimarkov_modules.py:153-155, 320-322);
+ *   - `end` is the EOS row of the augmented transition matrix (semimarkov_modules.py:462-471):
+ *     0 where a class may end the video, -1e9 otherwise; NULL = every class may end;
+ *   - `order` (optional) is the processing order of the videos, longest first, for load balance.
+ *
+ * Score of a segmentation:
+ *   init[c_0] + sum_i (len[l_i, c_i] + sum_{t in seg_i} em[t, c_i]) + sum_{i>=1} trans[c_i, c_{i-1}] + end[c_last]
+ */
+#ifndef HSMM_B200_H
+#define HSMM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HSMM_OK 0
+#define HSMM_ERR_ARG (-1)
+#define HSMM_ERR_SHAPE (-2)
+#define HSMM_ERR_CUDA (-3)
+
+/* Library version (major*100 + minor) and the last error message of the calling thread. */
+int hsmm_version(void);
+const char* hsmm_last_error(void);
+
+/*
+ * Emission scoring.  Replaces SemiMarkovModule._emission_log_probs_with_means / emission_log_probs
+ * (models/semimarkov/semimarkov_modules.py:324-381): per-frame tied-diagonal Gaussian log density
+ * of every valid class (+ additive narration constraints, semimarkov.py:227-232).
+ *
+ *   log N(x; mu_c, diag(var)) = x.w_c + bias_c + rowc(x),   w_c = mu_c / var,
+ *   bias_c = -0.5 sum_d mu_cd^2 / var_d,   rowc(x) = -0.5 sum_d x_d^2 / var_d + row_const,
+ *   row_const = -0.5 sum_d log var_d - 0.5 D log(2 pi).
+ *
+ * The class-independent part is kept apart so that the DP runs on well-conditioned numbers:
+ *   em[b,t,c]  = x.w_c + bias_c + penalty[b,t,c] - shift[b,t],  shift = max_c(...)   (<= 0, best class 0)
+ *   rowterm[b,t] = rowc(x_bt) + shift[b,t]        =>  elp[b,t,c] = em[b,t,c] + rowterm[b,t]
+ *   offset[b]  = sum_{t < lengths[b]} rowterm[b,t]   (double; added to logZ / Viterbi scores)
+ * Frames t >= lengths[b] get em = 0, rowterm = 0.
+ *
+ * X (B,Tmax,D); w (C,D); bias (C); inv_var (D); penalty (B,Tmax,C) or NULL;
+ * em (B,Tmax,ldc) out; rowterm (B,Tmax) out; offset (B) out (double, overwritten).
+ */
+int hsmm_emission(const float* X, const float* w, const float* bias, const float* inv_var, float row_const,
+                  const float* penalty, const int32_t* lengths, int B, int Tmax, int D, int C, int ldc,
+                  float* em, float* rowterm, double* offset, void* stream);
+
+/*
+ * Workspace sizes (bytes) for the DP entry points below, so that the caller allocates.
+ *   hsmm_viterbi_workspace_bytes : back-pointer table
+ *   hsmm_logz_saved_bytes        : forward quantities kept for hsmm_logz_backward
+ */
+size_t hsmm_viterbi_workspace_bytes(int B, int Tmax, int C, int K);
+size_t hsmm_logz_saved_bytes(int B, int Tmax, int C, int K);
+
+/*
+ * Max-plus Viterbi decode.  Replaces `SemiMarkovCRF(scores, lengths).argmax` +
+ * `SemiMarkovCRF.struct.from_parts` + the valid->global id remap
+ * (models/semimarkov/semimarkov_modules.py:660-696) and semimarkov_utils.spans_to_labels
+ * (semimarkov_utils.py:51-63), without materialising the (B,T,K,C+1,C+1) potentials of
+ * log_hsmm (semimarkov_modules.py:416-523).
+ *
+ * em (B,Tmax,ldc); init (C); trans (C,C) [to,from]; lenp (K,C) rows k=0..K-1; end (B,C) or NULL;
+ * offset (B) double or NULL; lengths (B); order (B) or NULL; class_ids (C+1) int32 or NULL
+ * (local -> global ids, last entry = EOS id; NULL = identity with EOS = C).
+ * out_spans (B,Tmax+1) int64: class id at segment starts, -1 inside segments and past the EOS,
+ *   EOS id at position lengths[b] (the reference's span encoding);
+ * out_labels (B,Tmax) int64 or NULL: per-frame class ids (frames >= lengths[b] get the EOS id);
+ * out_score (B) double or NULL: best path score (+ offset).
+ * workspace: hsmm_viterbi_workspace_bytes(...) bytes.
+ */
+int hsmm_viterbi(const float* em, int ldc, const float* init, const float* trans, const float* lenp,
+                 const float* end, const double* offset, const int32_t* lengths, const int32_t* order,
+                 const int32_t* class_ids, int B, int Tmax, int C, int K,
+                 int64_t* out_spans, int64_t* out_labels, double* out_score,
+                 void* workspace, void* stream);
+
+/*
+ * Log-semiring forward pass.  Replaces `SemiMarkovCRF(scores, lengths).partition`
+ * (models/semimarkov/semimarkov_modules.py:624,657): out_logz[b] = log sum over segmentations
+ * (+ offset[b]).  `saved` (hsmm_logz_saved_bytes) receives what the backward pass needs.
+ */
+int hsmm_logz_forward(const float* em, int ldc, const float* init, const float* trans, const float* lenp,
+                      const float* end, const double* offset, const int32_t* lengths, const int32_t* order,
+                      int B, int Tmax, int C, int K, double* out_logz, void* saved, void* stream);
+
+/*
+ * Backward pass / expected counts.  Replaces `loss.backward()` through pytorch-struct and log_hsmm
+ * (models/semimarkov/semimarkov.py:284-286): with grad_logz[b] = d loss / d logZ_b it ACCUMULATES
+ *   d_init (C)     += sum_b g_b * P(first segment has class c)
+ *   d_trans (C,C)  += sum_b g_b * E[# transitions c1 -> c2]            ([to,from])
+ *   d_len (K,C)    += sum_b g_b * E[# segments of class c and length k]
+ * and WRITES d_em (B,Tmax,ldc) = g_b * P(frame t has class c) (0 for t >= lengths[b]).
+ * Must follow hsmm_logz_forward with the same inputs and `saved` buffer.
+ */
+int hsmm_logz_backward(const float* em, int ldc, const float* init, const float* trans, const float* lenp,
+                       const float* end, const int32_t* lengths, const int32_t* order, const float* grad_logz,
+                       int B, int Tmax, int C, int K, const void* saved,
+                       float* d_init, float* d_trans, float* d_len, float* d_em, void* stream);
+
+/*
+ * Class-weighted feature sums.  The reduction behind d loss / d gaussian_means (autograd through
+ * emission_log_probs, semimarkov_modules.py:324-381) and behind the supervised class means
+ * r^T X of semimarkov_sufficient_stats (semimarkov_utils.py:74-126):
+ *   out_wx (C,D)  += sum_{b,t<len_b} weights[b,t,c] * X[b,t,:]
+ *   out_wsum (C)  += sum_{b,t<len_b} weights[b,t,c]
+ * weights (B,Tmax,ldc).  Both outputs are accumulated into (caller zeroes them).
+ */
+int hsmm_weighted_feature_sums(const float* X, const float* weights, int ldc, const int32_t* lengths,
+                               int B, int Tmax, int D, int C, float* out_wx, float* out_wsum, void* stream);
+
+/*
+ * Score of given (gold) segmentations.  Replaces `SemiMarkovCRF.struct.to_parts` + `struct().score`
+ * (models/semimarkov/semimarkov_modules.py:626-655) by a direct gather-sum over the segments.
+ * spans (B,Tmax) int32 in LOCAL class ids, -1 = continuation (semimarkov_utils.labels_to_spans).
+ * out_score (B) double (+ offset).  With grad_score != NULL it also accumulates the (one-hot) counts
+ * d_init/d_trans/d_len and writes d_em exactly like hsmm_logz_backward.
+ */
+int hsmm_gold_score(const float* em, int ldc, const float* init, const float* trans, const float* lenp,
+                    const float* end, const double* offset, const int32_t* lengths, const int32_t* spans,
+                    const float* grad_score, int B, int Tmax, int C, int K, double* out_score,
+                    float* d_init, float* d_trans, float* d_len, float* d_em, void* stream);
+
+/*
+ * Supervised sufficient statistics over labelled frames.  Replaces the numpy/sklearn pass of
+ * semimarkov_sufficient_stats + get_diagonal_covariances (semimarkov_utils.py:66-126):
+ *   out_sum_x (D) += sum x,  out_sum_x2 (D) += sum x^2   (double; tied diagonal variance)
+ * over the frames t < lengths[b].  Class sums use hsmm_weighted_feature_sums with one-hot weights.
+ */
+int hsmm_feature_moments(const float* X, const int32_t* lengths, int B, int Tmax, int D,
+                         double* out_sum_x, double* out_sum_x2, void* stream);
+
+/* One-hot weights from labels: weights[b,t,c] = (labels[b,t] == c) for t < lengths[b] else 0. */
+int hsmm_onehot_weights(const int32_t* labels, const int32_t* lengths, int B, int Tmax, int C, int ldc,
+                        float* weights, void* stream);
+
+/* Introspection used by tests/bench: name of the DP kernel variant picked for a shape
+ * ("reg<KR,S>/treg", "reg<KR,S>/tsmem", "ring") and how many kernels the library has launched. */
+const char* hsmm_dp_variant(int C, int K, int mode /*0 viterbi, 1 forward, 2 backward*/);
+uint64_t hsmm_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HSMM_B200_H */

@@ -1,0 +1,243 @@
+"""GPU parity tests: the CUDA path (through the C-ABI) against the oracle and the golden vectors."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import hsmm_oracle as O
+from oracle.module_oracle import from_golden, golden_addl_ends
+from tests.helpers import (check_viterbi_against_oracle, module_from_golden, random_problem, rel_err, to_dev)
+
+pytestmark = pytest.mark.gpu
+
+CASES = ["unconstrained", "short_clamp", "constrained", "constrained_narration"]
+KEYMAP = dict(g_means="gaussian_means", g_trans="transition_logits", g_init="init_logits", g_rates="poisson_log_rates")
+
+
+def _inputs(g):
+    feats = torch.from_numpy(g["features"]).cuda()
+    lengths = torch.from_numpy(g["lengths"]).long()
+    B = feats.shape[0]
+    vpi = None
+    if "valid_classes" in g:
+        vpi = [torch.from_numpy(g["valid_classes"]).long() for _ in range(B)]
+    cons = torch.from_numpy(g["constraints"]).cuda() if "constraints" in g else None
+    return feats, lengths, vpi, golden_addl_ends(g), cons
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_emission_golden(golden, case):
+    g = golden(case)
+    m = module_from_golden(g)
+    feats, lengths, vpi, addl, cons = _inputs(g)
+    elp = m.emission_log_probs(feats, None if vpi is None else vpi[0], cons).cpu().numpy()
+    for b, T in enumerate(g["lengths"]):
+        assert rel_err(elp[b, :T], g["elp"][b, :T]) < 1e-5
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_loglik_and_grads_golden(golden, case):
+    """logZ, its batch mean and the four parameter gradients: within 1e-4 relative of the reference's
+    fp32 values, and tighter against the fp64 oracle."""
+    g = golden(case)
+    m = module_from_golden(g)
+    feats, lengths, vpi, addl, cons = _inputs(g)
+    ll, log_det = m.log_likelihood(feats, lengths, vpi, spans=None, add_eos=True,
+                                   additional_allowed_ends_per_instance=addl, constraints=cons)
+    ll.backward()
+    assert abs(float(ll) - float(g["ll"])) <= 1e-4 * abs(float(g["ll"]))
+    assert float(log_det) == 0.0
+    r = from_golden(g).log_likelihood(g["features"], g["lengths"], g.get("valid_classes"), addl, g.get("constraints"))
+    assert abs(float(ll) - r["ll"]) <= 2e-6 * abs(r["ll"])
+    for gk, pk in KEYMAP.items():
+        mine = getattr(m, pk).grad.cpu().numpy()
+        assert rel_err(mine, g[gk]) < 1e-4, (gk, rel_err(mine, g[gk]))
+        assert rel_err(mine, r["grads"][pk]) < 1e-4, (gk, rel_err(mine, r["grads"][pk]))
+
+
+@pytest.mark.parametrize("case", CASES + ["supervised_decode"])
+def test_viterbi_golden(golden, case):
+    g = golden(case)
+    m = module_from_golden(g)
+    feats, lengths, vpi, addl, cons = _inputs(g)
+    spans, labels = m.viterbi(feats, lengths, vpi, add_eos=True, additional_allowed_ends_per_instance=addl,
+                              constraints=cons, return_labels=True)
+    assert spans.dtype == torch.int64 and not spans.is_cuda
+    ref = g["viterbi_spans"]
+    if not (spans.numpy() == ref).all():
+        # only a numerical near-tie may differ: compare fp64 path scores through the oracle
+        o_spans, best, aux = from_golden(g).viterbi(g["features"], g["lengths"], g.get("valid_classes"), addl, g.get("constraints"))
+        prob = dict(em=aux["em"], lengths=g["lengths"], init=aux["init"], trans=aux["trans"], lenp=aux["lenp"], end=aux["ends"])
+        n_cls = m.n_classes
+        table = {int(c): i for i, c in enumerate(g["valid_classes"])} if "valid_classes" in g else {i: i for i in range(n_cls)}
+        table[n_cls] = aux["em"].shape[-1]
+        table[-1] = -1
+        local = np.vectorize(table.get)(spans.numpy())
+        check_viterbi_against_oracle(prob, local, em_round=False)
+    # per-frame labels agree with the span encoding
+    import action_segmentation_b200 as pkg
+    lab_ref = pkg.semimarkov_utils.spans_to_labels(spans)
+    for b, T in enumerate(g["lengths"]):
+        assert (labels[b, :T] == lab_ref[b, :T]).all()
+
+
+def test_known_answer(golden):
+    """Body of the reference's test_log_hsmm (models/test_semimarkov.py:266-323) through hsmm_viterbi."""
+    import action_segmentation_b200 as pkg
+    g = golden("known_answer")
+    b, C, N, K, step = (int(g[k]) for k in ("b", "C", "N", "K", "step"))
+    padded = N + 2 * step
+    em = np.full((b, padded, C), O.BIG_NEG)
+    for n in range(padded):
+        em[:, n, (n // step) % C] = 1
+    init = np.full(C, O.BIG_NEG)
+    init[0] = 0
+    lenp = np.full((K, C), O.BIG_NEG)
+    lenp[step] = 0
+    prob = dict(em=em, lengths=g["lengths_unpadded"], init=init, trans=np.zeros((C, C)), lenp=lenp, end=None)
+    d = to_dev(prob)
+    spans, labels, score = pkg.hsmm.viterbi_decode(d["em"], C, d["init"], d["trans"], d["lenp"], None, None,
+                                                   d["lengths_i32"], d["order"])
+    assert (spans.cpu().numpy() == g["sequence"]).all()
+    for s in range(N // step):
+        assert (spans[:, step * s].cpu() == s % C).all()
+
+
+SHAPES = [
+    # (B, Tmax, C, K, chain, ends)  -- one per compiled DP variant / layout regime
+    (9, 60, 23, 20, True, True),     # reg<20,1> trans-reg  (flagship CrossTask shape)
+    (9, 60, 9, 20, True, True),      # reg<10,2> trans-reg
+    (7, 150, 11, 100, False, False),  # reg<25,4> trans-smem, 2 warps
+    (5, 150, 23, 100, True, True),   # reg<25,4> trans-smem, 3 warps
+    (5, 120, 16, 50, False, False),  # reg<25,2> trans-reg
+    (4, 120, 64, 50, False, False),  # reg<25,2> trans-smem 4 warps
+    (3, 90, 133, 50, False, False),  # reg<25,2> 9 warps
+    (3, 220, 133, 200, False, False),  # reg<50,4> len-smem 17 warps
+    (3, 260, 64, 200, False, False),  # reg<25,8> 16 warps
+    (2, 520, 48, 500, False, False),  # reg<63,8> len-smem
+    (6, 40, 3, 30, False, False),    # reg<32,1>
+    (6, 70, 5, 52, False, False),    # reg<13,4>
+    (4, 30, 1, 5, False, False),     # single class
+    (5, 12, 4, 40, False, False),    # K clamped to the padded length
+]
+
+
+@pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "B%d_T%d_C%d_K%d" % s[:4])
+def test_viterbi_random_vs_oracle(shape):
+    import action_segmentation_b200 as pkg
+    B, Tmax, C, K, chain, ends = shape
+    rng = np.random.default_rng(100 + C * 7 + K)
+    prob = random_problem(rng, B, Tmax, C, K, Tmin=1, chain=chain, ends=ends)
+    prob["lenp"] = O.clamp_len_table(prob["lenp"], Tmax)
+    d = to_dev(prob)
+    spans, labels, score = pkg.hsmm.viterbi_decode(d["em"], C, d["init"], d["trans"], d["lenp"], d["end"], None,
+                                                   d["lengths_i32"], d["order"])
+    n_exact = check_viterbi_against_oracle(prob, spans.cpu().numpy(), score.cpu().numpy())
+    assert n_exact >= B - 1, "more than one video differs from the oracle path (%d of %d exact)" % (n_exact, B)
+
+
+@pytest.mark.parametrize("shape", SHAPES[:7] + SHAPES[10:], ids=lambda s: "B%d_T%d_C%d_K%d" % s[:4])
+def test_logz_and_counts_random_vs_oracle(shape):
+    """logZ within 1e-5 relative, expected counts within 1e-4 relative of the fp64 oracle."""
+    import action_segmentation_b200 as pkg
+    B, Tmax, C, K, chain, ends = shape
+    rng = np.random.default_rng(200 + C * 7 + K)
+    prob = random_problem(rng, B, Tmax, C, K, Tmin=1, chain=chain, ends=ends)
+    prob["lenp"] = O.clamp_len_table(prob["lenp"], Tmax)
+    d = to_dev(prob)
+    logz, saved = pkg.hsmm.logz_forward(d["em"], C, d["init"], d["trans"], d["lenp"], d["end"], None, d["lengths_i32"], d["order"])
+    w = rng.uniform(0.5, 1.5, size=B)
+    g = torch.from_numpy(w).float().cuda()
+    d_init, d_trans, d_len, d_em = pkg.hsmm.logz_backward(d["em"], C, d["init"], d["trans"], d["lenp"], d["end"],
+                                                         d["lengths_i32"], d["order"], g, saved)
+    f32 = lambda x: x.astype(np.float32).astype(np.float64)  # noqa: E731
+    ref_logz, acc = O.batch_logz_and_counts(f32(prob["em"]), prob["lengths"], f32(prob["init"]), f32(prob["trans"]),
+                                            f32(prob["lenp"]), prob["end"], w)
+    assert np.allclose(logz.cpu().numpy(), ref_logz, rtol=1e-5, atol=1e-4)
+    assert rel_err(d_init.cpu().numpy(), acc["E_init"]) < 1e-4
+    assert rel_err(d_trans.cpu().numpy(), acc["E_trans"]) < 1e-4
+    assert rel_err(d_len.cpu().numpy(), acc["E_len"]) < 1e-4
+    assert rel_err(d_em.cpu().numpy()[:, :, :C], acc["E_em"]) < 1e-4
+
+
+def test_supervised_fit_golden(golden):
+    """fit_supervised closed form (semimarkov_modules.py:195-256) against the reference's fitted parameters."""
+    import action_segmentation_b200 as pkg
+    from tests.golden.ref_import import RefArgs
+    g = golden("supervised_fit")
+    C, K = int(g["n_classes"]), int(g["max_k"])
+    D = g["features"].shape[1]
+    m = pkg.SemiMarkovModule(RefArgs(sm_max_span_length=K), C, D, allow_self_transitions=True).cuda()
+    feats, labels, off = [], [], 0
+    for n in g["lengths"]:
+        feats.append(torch.from_numpy(g["features"][off:off + n]))
+        labels.append(torch.from_numpy(g["labels"][off:off + n]))
+        off += n
+    m.fit_supervised(feats, labels)
+    for k in ("gaussian_means", "gaussian_cov", "transition_logits", "init_logits", "poisson_log_rates"):
+        assert rel_err(getattr(m, k).detach().cpu().numpy(), g[k]) < 2e-5, k
+
+
+def test_gold_score_golden(golden):
+    """log_likelihood with gold spans, generative and discriminative (semimarkov_modules.py:626-655)."""
+    g = golden("gold_score")
+    for tag, disc in (("gen", False), ("disc", True)):
+        m = module_from_golden(g, sm_train_discriminatively=disc)
+        feats = torch.from_numpy(g["features"]).cuda()
+        lengths = torch.from_numpy(g["lengths"]).long()
+        spans = torch.from_numpy(g["spans"]).long()
+        ll, _ = m.log_likelihood(feats, lengths, None, spans=spans, add_eos=True)
+        ll.backward()
+        assert abs(float(ll) - float(g["ll_" + tag])) <= 1e-4 * abs(float(g["ll_" + tag])), tag
+        for gk, pk in KEYMAP.items():
+            mine = getattr(m, pk).grad.cpu().numpy()
+            assert rel_err(mine, g[gk + "_" + tag]) < 1e-4, (tag, gk)
+
+
+def test_full_size_properties():
+    """BASELINE-size batch (CrossTask shape: D=200, C=23, K=20, T up to 3000): size-independent
+    invariants of the DP outputs."""
+    import action_segmentation_b200 as pkg
+    from tests.golden.ref_import import RefArgs
+    torch.manual_seed(5)
+    B, Tmax, D, C, K = 64, 3000, 200, 23, 20
+    m = pkg.SemiMarkovModule(RefArgs(sm_max_span_length=K), C, D, allow_self_transitions=True).cuda()
+    with torch.no_grad():
+        m.gaussian_means.normal_(0, 0.3)
+        m.poisson_log_rates.uniform_(1.0, 2.5)
+        m.transition_logits.normal_()
+    lengths = torch.randint(1000, Tmax + 1, (B,))
+    lengths[0] = Tmax
+    lab = torch.randint(0, C, (B, Tmax // 10 + 1)).repeat_interleave(10, dim=1)[:, :Tmax].cuda()
+    feats = m.gaussian_means.detach()[lab] + torch.randn(B, Tmax, D, device="cuda")
+    s = m._scores(feats, lengths, None, None)
+    em, rowterm, offset = pkg.hsmm.emission_scores(feats, s["means"], s["cov_diag"], None, s["lengths_i32"])
+    assert float(em[:, :, :C].max()) <= 0.0 + 1e-6  # shifted by the per-frame best class
+    logz, saved = pkg.hsmm.logz_forward(em, C, s["init"], s["trans"], s["lenp"], None, offset, s["lengths_i32"], s["order"])
+    g = torch.ones(B, device="cuda")
+    d_init, d_trans, d_len, d_em = pkg.hsmm.logz_backward(em, C, s["init"].detach(), s["trans"].detach(), s["lenp"].detach(),
+                                                         None, s["lengths_i32"], s["order"], g, saved)
+    spans, labels, score = pkg.hsmm.viterbi_decode(em, C, s["init"], s["trans"], s["lenp"], None, offset,
+                                                   s["lengths_i32"], s["order"])
+    lens_dev = lengths.cuda()
+    mask = (torch.arange(Tmax, device="cuda")[None] < lens_dev[:, None]).float()
+    # posterior over classes sums to one on every real frame, zero on padding
+    assert torch.allclose(d_em[:, :, :C].sum(-1), mask, atol=2e-4)
+    # one first segment per video; expected segment lengths add up to the number of frames
+    assert abs(float(d_init.sum()) - B) < 1e-3 * B
+    k = torch.arange(K, device="cuda", dtype=torch.float32)[:, None]
+    assert abs(float((d_len * k).sum()) - float(lengths.sum())) < 1e-4 * float(lengths.sum())
+    # segments = transitions + one per video
+    assert abs(float(d_len.sum()) - float(d_trans.sum()) - B) < 1e-4 * float(d_len.sum())
+    # max-plus <= log-sum; decoded labels agree with spans; spans only start valid segments
+    assert (score <= logz + 1e-6 * logz.abs()).all()
+    lab_ref = pkg.semimarkov_utils.spans_to_labels(spans)
+    assert (torch.where(mask.bool(), labels, 0) == torch.where(mask.bool(), lab_ref[:, :Tmax], 0)).all()
+    assert (spans[torch.arange(B), lens_dev] == C).all()
+    # fp64 score of the decoded path equals the kernel's score (three videos, oracle as checker)
+    em_h, off_h = em.cpu().numpy().astype(np.float64), offset.cpu().numpy()
+    for b in (0, 1, B - 1):
+        T = int(lengths[b])
+        segs = O.segments_from_spans(spans[b].cpu().numpy(), T)
+        sc = O.path_score(segs, em_h[b, :T, :C], s["init"].detach().cpu().numpy().astype(np.float64),
+                          s["trans"].detach().cpu().numpy().astype(np.float64), s["lenp"].detach().cpu().numpy().astype(np.float64))
+        assert abs(sc + off_h[b] - float(score[b])) < 1e-6 * abs(float(score[b]))
