@@ -73,6 +73,7 @@ static int check_dims(const char* fn, int B, int Tmax, int C, int K, int ldc) {
 struct Saved {  // layout of the `saved` buffer of hsmm_logz_forward
     float* fbeta;
     float* fgamma;
+    float* fdelta;
     float* logz2;
 };
 static size_t plane_elems(int B, int Tmax, int C) { return (size_t)B * (Tmax + 1) * (size_t)((C + 3) / 4 * 4); }
@@ -81,7 +82,8 @@ static Saved carve(void* saved, int B, int Tmax, int C) {
     const size_t n = plane_elems(B, Tmax, C);
     s.fbeta = reinterpret_cast<float*>(saved);
     s.fgamma = s.fbeta + n;
-    s.logz2 = s.fgamma + n;
+    s.fdelta = s.fgamma + n;
+    s.logz2 = s.fdelta + (size_t)B * (Tmax + 1);
     return s;
 }
 
@@ -108,7 +110,7 @@ size_t hsmm_viterbi_workspace_bytes(int B, int Tmax, int C, int K) {
 
 size_t hsmm_logz_saved_bytes(int B, int Tmax, int C, int K) {
     (void)K;
-    return (2 * plane_elems(B, Tmax, C) + (size_t)B + 4) * sizeof(float);
+    return (2 * plane_elems(B, Tmax, C) + (size_t)B * (Tmax + 1) + (size_t)B + 4) * sizeof(float);
 }
 
 int hsmm_emission(const float* X, const float* w, const float* bias, const float* inv_var, float row_const,
@@ -173,7 +175,7 @@ int hsmm_logz_forward(const float* em, int ldc, const float* init, const float* 
     p.em = em; p.init = init; p.trans = trans; p.lenp = lenp; p.end = end; p.offset = offset;
     p.lengths = lengths; p.order = order; p.B = B; p.Tmax = Tmax; p.C = C; p.L = K - 1; p.ldc = ldc;
     Saved s = carve(saved, B, Tmax, C);
-    p.fbeta = s.fbeta; p.fgamma = s.fgamma; p.logz2 = s.logz2; p.logz = out_logz;
+    p.fbeta = s.fbeta; p.fgamma = s.fgamma; p.fdelta = s.fdelta; p.logz2 = s.logz2; p.logz = out_logz;
     if (!dp_reg_supported(C, p.L, 1)) {
         set_error("hsmm_logz_forward: shape C=%d K=%d not supported (register-resident DP only)", C, K);
         return HSMM_ERR_SHAPE;
@@ -195,7 +197,7 @@ int hsmm_logz_backward(const float* em, int ldc, const float* init, const float*
     p.em = em; p.init = init; p.trans = trans; p.lenp = lenp; p.end = end;
     p.lengths = lengths; p.order = order; p.B = B; p.Tmax = Tmax; p.C = C; p.L = K - 1; p.ldc = ldc;
     Saved s = carve(const_cast<void*>(saved), B, Tmax, C);
-    p.fbeta = s.fbeta; p.fgamma = s.fgamma; p.logz2 = s.logz2;
+    p.fbeta = s.fbeta; p.fgamma = s.fgamma; p.fdelta = s.fdelta; p.logz2 = s.logz2;
     p.grad = grad_logz; p.d_init = d_init; p.d_trans = d_trans; p.d_len = d_len; p.d_em = d_em;
     if (!dp_reg_supported(C, p.L, 2)) {
         set_error("hsmm_logz_backward: shape C=%d K=%d not supported (register-resident DP only)", C, K);

@@ -106,7 +106,8 @@ struct DpParams {
     // forward
     float* fbeta;   // (B, Tmax+1, ldc)  beta[n], n = 0..T-1   (log2 domain)
     float* fgamma;  // (B, Tmax+1, ldc)  gamma[n], n = 1..T    (log2 domain)
-    float* logz2;   // (B) log2-domain logZ without offset
+    float* fdelta;  // (B, Tmax+1)  per-frame normaliser increments delta_n, n = 1..T
+    float* logz2;   // (B) log2 Z relative to the accumulated normaliser nu_T
     double* logz;   // (B)
     // backward
     const float* grad;  // (B)

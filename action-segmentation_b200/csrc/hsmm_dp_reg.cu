@@ -117,6 +117,11 @@ __global__ void __launch_bounds__(MAXT) dp_forward_kernel(const DpParams p) {
     const size_t row0 = (size_t)b * (Tmax + 1);
     if (!VIT && owner) p.fbeta[row0 * ldc + c] = beta;
 
+    // Running normaliser: every stored quantity of frame n is relative to nu_n = sum_{m<=n} delta_m,
+    // delta_n = max_c gamma~[n-1][c] (lagged), so values stay O(1) however long the video is.
+    float delta = 0.0f;
+    double nu = 0.0;
+
     float enext[F];
 #pragma unroll
     for (int f = 0; f < F; ++f) enext[f] = (valid && f < T) ? __ldg(em_b + (size_t)f * ldc + c) : 0.0f;
@@ -134,7 +139,9 @@ __global__ void __launch_bounds__(MAXT) dp_forward_kernel(const DpParams p) {
         for (int f = 0; f < F; ++f) {
             const int n = n0 + f;
             if (n > T) break;
-            const float e = ecur[f] * SC;
+            const float e = ecur[f] * SC - delta;
+            nu += (double)delta;
+            if (!VIT && gtid == 0) p.fdelta[row0 + n] = delta;
             // ---- shift-and-add the span window --------------------------------------------
             float carry = 0.0f;
             if (S > 1) carry = __shfl_up_sync(FULL, A[KR - 1], CPW);
@@ -177,6 +184,7 @@ __global__ void __launch_bounds__(MAXT) dp_forward_kernel(const DpParams p) {
                 break;
             }
             // ---- phase 2: transitions -----------------------------------------------------
+            float gm = NEG;
             if constexpr (VIT) {
                 float best = NEG;
                 int bc = j;
@@ -185,7 +193,9 @@ __global__ void __launch_bounds__(MAXT) dp_forward_kernel(const DpParams p) {
                     for (int i = 0; i < CRR; ++i) {
                         const int c1 = i * S + j;
                         if (c1 < C) {
-                            const float v = gs[c1] + tr[i];
+                            const float gv = gs[c1];
+                            gm = fmaxf(gm, gv);
+                            const float v = gv + tr[i];
                             if (v > best || i == 0) {
                                 best = v;
                                 bc = c1;
@@ -194,7 +204,9 @@ __global__ void __launch_bounds__(MAXT) dp_forward_kernel(const DpParams p) {
                     }
                 } else {
                     for (int c1 = j; c1 < C; c1 += S) {
-                        const float v = gs[c1] + transT[c1 * ldT + c];
+                        const float gv = gs[c1];
+                        gm = fmaxf(gm, gv);
+                        const float v = gv + transT[c1 * ldT + c];
                         if (v > best || c1 == j) {
                             best = v;
                             bc = c1;
@@ -210,10 +222,18 @@ __global__ void __launch_bounds__(MAXT) dp_forward_kernel(const DpParams p) {
 #pragma unroll
                     for (int i = 0; i < CRR; ++i) {
                         const int c1 = i * S + j;
-                        if (c1 < C) m = fmaxf(m, gs[c1] + tr[i]);
+                        if (c1 < C) {
+                            const float gv = gs[c1];
+                            gm = fmaxf(gm, gv);
+                            m = fmaxf(m, gv + tr[i]);
+                        }
                     }
                 } else {
-                    for (int c1 = j; c1 < C; c1 += S) m = fmaxf(m, gs[c1] + transT[c1 * ldT + c]);
+                    for (int c1 = j; c1 < C; c1 += S) {
+                        const float gv = gs[c1];
+                        gm = fmaxf(gm, gv);
+                        m = fmaxf(m, gv + transT[c1 * ldT + c]);
+                    }
                 }
                 m = slice_max<S>(m);
                 float s = 0.0f;
@@ -231,6 +251,7 @@ __global__ void __launch_bounds__(MAXT) dp_forward_kernel(const DpParams p) {
                 if (owner) p.fbeta[(row0 + n) * ldc + c] = beta;
             }
             if (!valid) beta = NEG;
+            delta = slice_max<S>(gm);
         }
     }
 
@@ -246,9 +267,9 @@ __global__ void __launch_bounds__(MAXT) dp_forward_kernel(const DpParams p) {
             for (int cc = lane; cc < C; cc += 32) s += ex2(gT[cc] + (endb ? endb[cc] * SC : 0.0f) - m);
             s = warp_sum(s);
             if (lane == 0) {
-                const float lz2 = m + lg2(s);
-                p.logz2[b] = lz2;
-                p.logz[b] = (double)lz2 * LN2 + (p.offset ? p.offset[b] : 0.0);
+                const float lzrel = m + lg2(s);  // relative to nu_T
+                p.logz2[b] = lzrel;
+                p.logz[b] = (nu + (double)lzrel) * LN2 + (p.offset ? p.offset[b] : 0.0);
             }
         }
     } else {
@@ -279,7 +300,7 @@ __global__ void __launch_bounds__(MAXT) dp_forward_kernel(const DpParams p) {
                 bc = oc;
             }
         }
-        if (lane == 0 && p.score) p.score[b] = (double)best + (p.offset ? p.offset[b] : 0.0);
+        if (lane == 0 && p.score) p.score[b] = nu + (double)best + (p.offset ? p.offset[b] : 0.0);
         int n = T, cc = bc;
         while (n > 0) {
             const uint32_t v = __ldcg(p.bp + (row0 + n) * ldc + cc);
@@ -381,7 +402,7 @@ __global__ void __launch_bounds__(MAXT) dp_backward_kernel(const DpParams p) {
         }
     }
     const float endc = valid ? (p.end ? p.end[(size_t)b * C + c] : 0.0f) * SC : NEG;
-    const float lz = p.logz2[b];
+    const float lzrel = p.logz2[b];  // log2 Z relative to nu_T
     const float w = p.grad[b];
     const float init_c = valid ? p.init[c] * SC : NEG;
 
@@ -390,36 +411,42 @@ __global__ void __launch_bounds__(MAXT) dp_backward_kernel(const DpParams p) {
     const float* fb = p.fbeta + row0 * ldc;
     const float* fg = p.fgamma + row0 * ldc;
     float* dem = p.d_em + (size_t)b * Tmax * ldc;
+    const float* fd = p.fdelta + row0;
 
-    float eta = endc;
+    // backward quantities of frame n are relative to mu_n = logZ - nu_n (see the forward kernel), so
+    // posteriors are exp(forward~ + backward~) of O(1) numbers.
+    float eta = valid ? endc - lzrel : NEG;
     float occ = 0.0f, comp = 0.0f;  // Kahan-compensated occupancy
-    float Fprev = valid ? w * ex2(__ldg(fg + (size_t)T * ldc + c) + endc - lz) : 0.0f;
+    float Fprev = valid ? w * ex2(__ldg(fg + (size_t)T * ldc + c) + endc - lzrel) : 0.0f;
     float Sprev = 0.0f;
 
     // frames beyond the video: zero gradient
     for (int i = T * ldc + gtid; i < Tmax * ldc; i += G) dem[i] = 0.0f;
 
-    float enext[F], bnext[F], gnext[F];
+    float enext[F], bnext[F], gnext[F], dnext[F];
 #pragma unroll
     for (int f = 0; f < F; ++f) {
         const int n = T - 1 - f;
         const bool ok = valid && n >= 0;
+        dnext[f] = (n >= 0) ? __ldg(fd + n + 1) : 0.0f;
         enext[f] = ok ? __ldg(em_b + (size_t)n * ldc + c) : 0.0f;
         bnext[f] = (ok && n > 0) ? __ldg(fb + (size_t)n * ldc + c) : 0.0f;
         gnext[f] = (ok && n > 0) ? __ldg(fg + (size_t)n * ldc + c) : 0.0f;
     }
     for (int n0 = T - 1; n0 >= 0; n0 -= F) {
-        float ecur[F], bcur[F], gcur[F];
+        float ecur[F], bcur[F], gcur[F], dcur[F];
 #pragma unroll
         for (int f = 0; f < F; ++f) {
             ecur[f] = enext[f];
             bcur[f] = bnext[f];
             gcur[f] = gnext[f];
+            dcur[f] = dnext[f];
         }
 #pragma unroll
         for (int f = 0; f < F; ++f) {
             const int n = n0 - F - f;
             const bool ok = valid && n >= 0;
+            dnext[f] = (n >= 0) ? __ldg(fd + n + 1) : 0.0f;
             enext[f] = ok ? __ldg(em_b + (size_t)n * ldc + c) : 0.0f;
             bnext[f] = (ok && n > 0) ? __ldg(fb + (size_t)n * ldc + c) : 0.0f;
             gnext[f] = (ok && n > 0) ? __ldg(fg + (size_t)n * ldc + c) : 0.0f;
@@ -428,7 +455,7 @@ __global__ void __launch_bounds__(MAXT) dp_backward_kernel(const DpParams p) {
         for (int f = 0; f < F; ++f) {
             const int n = n0 - f;
             if (n < 0) break;
-            const float e = ecur[f] * SC;
+            const float e = ecur[f] * SC - dcur[f];
             float carry = 0.0f;
             if (S > 1) carry = __shfl_up_sync(FULL, Bq[KR - 1], CPW);
 #pragma unroll
@@ -440,7 +467,7 @@ __global__ void __launch_bounds__(MAXT) dp_backward_kernel(const DpParams p) {
             for (int i = 1; i < KR; ++i) m = fmaxf(m, Bq[i] + LN(i));
             m = slice_max<S>(m);
             const float betan = (n == 0) ? init_c : bcur[f];
-            const float coef = valid ? w * ex2(betan + m - lz) : 0.0f;
+            const float coef = valid ? w * ex2(betan + m) : 0.0f;
             float s = 0.0f;
 #pragma unroll
             for (int i = 0; i < KR; ++i) {
@@ -479,7 +506,7 @@ __global__ void __launch_bounds__(MAXT) dp_backward_kernel(const DpParams p) {
                 for (int c2 = j; c2 < C; c2 += S) m2 = fmaxf(m2, zs[c2] + trans_s[c2 * ldT + c]);
             }
             m2 = slice_max<S>(m2);
-            const float coef2 = valid ? w * ex2(gcur[f] + m2 - lz) : 0.0f;
+            const float coef2 = valid ? w * ex2(gcur[f] + m2) : 0.0f;
             float s2 = 0.0f;
             if constexpr (TREG) {
 #pragma unroll
@@ -536,7 +563,9 @@ static const RegVariant kVariants[] = {
     {50, 4, false}, {50, 8, false}, {63, 8, false},
 };
 constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
-constexpr int kMaxThreadsSmallTreg = 128, kMaxThreadsSmall = 512, kMaxThreadsBig = 576, kMaxThreadsBigBwd = 384;
+constexpr int kMaxThreadsSmallTreg = 128, kMaxThreadsSmall = 512;
+// long windows keep KR partial scores per thread: fewer threads per CTA so that they stay in registers
+constexpr int max_threads_big(int KR, int mode) { return mode == 2 ? (KR > 50 ? 256 : 384) : (KR > 50 ? 384 : 576); }
 
 struct RegChoice {
     int v;      // variant index, -1 = none
@@ -564,8 +593,7 @@ static RegChoice choose(int C, int L, int mode) {
         const int cpw = 32 / rv.S;
         const int W = (C + cpw - 1) / cpw;
         const bool treg = rv.lreg && (W == 1);
-        const int maxt = rv.lreg ? (treg ? kMaxThreadsSmallTreg : kMaxThreadsSmall)
-                                 : (mode == 2 ? kMaxThreadsBigBwd : kMaxThreadsBig);
+        const int maxt = rv.lreg ? (treg ? kMaxThreadsSmallTreg : kMaxThreadsSmall) : max_threads_big(rv.KR, mode);
         if (W * 32 > maxt) continue;
         int vpb = treg ? 4 : maxt / (W * 32);
         if (vpb > 8) vpb = 8;
@@ -616,7 +644,7 @@ static int launch_small(const DpParams& p, const RegChoice& ch, cudaStream_t st)
 }
 template <int MODE, int KR, int S>
 static int launch_big(const DpParams& p, const RegChoice& ch, cudaStream_t st) {
-    return launch_one<MODE, KR, S, false, false, (MODE == 2 ? kMaxThreadsBigBwd : kMaxThreadsBig)>(p, ch, st);
+    return launch_one<MODE, KR, S, false, false, max_threads_big(KR, MODE)>(p, ch, st);
 }
 
 template <int MODE>

