@@ -39,8 +39,8 @@ static int num_sms() {
 }
 
 // implemented in the kernel translation units
-bool dp_reg_supported(int C, int L, int mode);
-const char* dp_reg_name(int C, int L, int mode);
+bool dp_reg_supported(int C, int L, int mode, bool sparse);
+const char* dp_reg_name(int C, int L, int mode, bool sparse);
 int dp_reg_launch(DpParams p, int mode, cudaStream_t st);
 int launch_emission(const float*, const float*, const float*, const float*, float, const float*, const int32_t*, int, int, int,
                     int, int, float*, float*, double*, cudaStream_t);
@@ -75,6 +75,7 @@ struct Saved {  // layout of the `saved` buffer of hsmm_logz_forward
     float* fgamma;
     float* fdelta;
     float* logz2;
+    float* fflag;
 };
 static size_t plane_elems(int B, int Tmax, int C) { return (size_t)B * (Tmax + 1) * (size_t)((C + 3) / 4 * 4); }
 static Saved carve(void* saved, int B, int Tmax, int C) {
@@ -84,6 +85,7 @@ static Saved carve(void* saved, int B, int Tmax, int C) {
     s.fgamma = s.fbeta + n;
     s.fdelta = s.fgamma + n;
     s.logz2 = s.fdelta + (size_t)B * (Tmax + 1);
+    s.fflag = s.logz2 + B;
     return s;
 }
 
@@ -97,9 +99,9 @@ int hsmm_version(void) { return 100; }
 const char* hsmm_last_error(void) { return g_err; }
 uint64_t hsmm_launch_count(void) { return g_launches.load(); }
 
-const char* hsmm_dp_variant(int C, int K, int mode) {
+const char* hsmm_dp_variant(int C, int K, int mode, int sparse) {
     const int L = K - 1;
-    if (dp_reg_supported(C, L, mode)) return dp_reg_name(C, L, mode);
+    if (dp_reg_supported(C, L, mode, sparse != 0)) return dp_reg_name(C, L, mode, sparse != 0);
     return "unsupported";
 }
 
@@ -110,7 +112,7 @@ size_t hsmm_viterbi_workspace_bytes(int B, int Tmax, int C, int K) {
 
 size_t hsmm_logz_saved_bytes(int B, int Tmax, int C, int K) {
     (void)K;
-    return (2 * plane_elems(B, Tmax, C) + (size_t)B * (Tmax + 1) + (size_t)B + 4) * sizeof(float);
+    return (2 * plane_elems(B, Tmax, C) + (size_t)B * (Tmax + 1) + 2 * (size_t)B + 4) * sizeof(float);
 }
 
 int hsmm_emission(const float* X, const float* w, const float* bias, const float* inv_var, float row_const,
@@ -132,8 +134,8 @@ int hsmm_emission(const float* X, const float* w, const float* bias, const float
                            (cudaStream_t)stream);
 }
 
-int hsmm_viterbi(const float* em, int ldc, const float* init, const float* trans, const float* lenp, const float* end,
-                 const double* offset, const int32_t* lengths, const int32_t* order, const int32_t* class_ids, int B,
+int hsmm_viterbi(const float* em, int ldc, const float* init, const float* trans, const int32_t* trans_pred, const float* lenp,
+                 const float* end, const double* offset, const int32_t* lengths, const int32_t* order, const int32_t* class_ids, int B,
                  int Tmax, int C, int K, int64_t* out_spans, int64_t* out_labels, double* out_score, void* workspace,
                  void* stream) {
     if (!em || !init || !trans || !lenp || !lengths || !out_spans || !workspace) {
@@ -151,14 +153,14 @@ int hsmm_viterbi(const float* em, int ldc, const float* init, const float* trans
     p.em = em; p.init = init; p.trans = trans; p.lenp = lenp; p.end = end; p.offset = offset;
     p.lengths = lengths; p.order = order; p.B = B; p.Tmax = Tmax; p.C = C; p.L = K - 1; p.ldc = ldc;
     p.bp = reinterpret_cast<uint32_t*>(workspace); p.class_ids = class_ids; p.spans = out_spans; p.labels = out_labels;
-    p.score = out_score;
-    if (dp_reg_supported(C, p.L, 0)) return dp_reg_launch(p, 0, (cudaStream_t)stream);
+    p.score = out_score; p.trans_pred = trans_pred;
+    if (dp_reg_supported(C, p.L, 0, trans_pred != nullptr)) return dp_reg_launch(p, 0, (cudaStream_t)stream);
     set_error("hsmm_viterbi: shape C=%d K=%d exceeds on-chip capacity", C, K);
     return HSMM_ERR_SHAPE;
 }
 
-int hsmm_logz_forward(const float* em, int ldc, const float* init, const float* trans, const float* lenp, const float* end,
-                      const double* offset, const int32_t* lengths, const int32_t* order, int B, int Tmax, int C, int K,
+int hsmm_logz_forward(const float* em, int ldc, const float* init, const float* trans, const int32_t* trans_pred, const float* lenp,
+                      const float* end, const double* offset, const int32_t* lengths, const int32_t* order, int B, int Tmax, int C, int K,
                       double* out_logz, void* saved, void* stream) {
     if (!em || !init || !trans || !lenp || !lengths || !out_logz || !saved) {
         set_error("hsmm_logz_forward: null pointer");
@@ -175,16 +177,17 @@ int hsmm_logz_forward(const float* em, int ldc, const float* init, const float* 
     p.em = em; p.init = init; p.trans = trans; p.lenp = lenp; p.end = end; p.offset = offset;
     p.lengths = lengths; p.order = order; p.B = B; p.Tmax = Tmax; p.C = C; p.L = K - 1; p.ldc = ldc;
     Saved s = carve(saved, B, Tmax, C);
-    p.fbeta = s.fbeta; p.fgamma = s.fgamma; p.fdelta = s.fdelta; p.logz2 = s.logz2; p.logz = out_logz;
-    if (!dp_reg_supported(C, p.L, 1)) {
+    p.fbeta = s.fbeta; p.fgamma = s.fgamma; p.fdelta = s.fdelta; p.logz2 = s.logz2; p.fflag = s.fflag; p.logz = out_logz;
+    p.trans_pred = trans_pred;
+    if (!dp_reg_supported(C, p.L, 1, trans_pred != nullptr)) {
         set_error("hsmm_logz_forward: shape C=%d K=%d not supported (register-resident DP only)", C, K);
         return HSMM_ERR_SHAPE;
     }
     return dp_reg_launch(p, 1, (cudaStream_t)stream);
 }
 
-int hsmm_logz_backward(const float* em, int ldc, const float* init, const float* trans, const float* lenp, const float* end,
-                       const int32_t* lengths, const int32_t* order, const float* grad_logz, int B, int Tmax, int C, int K,
+int hsmm_logz_backward(const float* em, int ldc, const float* init, const float* trans, const int32_t* trans_succ, const float* lenp,
+                       const float* end, const int32_t* lengths, const int32_t* order, const float* grad_logz, int B, int Tmax, int C, int K,
                        const void* saved, float* d_init, float* d_trans, float* d_len, float* d_em, void* stream) {
     if (!em || !init || !trans || !lenp || !lengths || !grad_logz || !saved || !d_init || !d_trans || !d_len || !d_em) {
         set_error("hsmm_logz_backward: null pointer");
@@ -197,9 +200,10 @@ int hsmm_logz_backward(const float* em, int ldc, const float* init, const float*
     p.em = em; p.init = init; p.trans = trans; p.lenp = lenp; p.end = end;
     p.lengths = lengths; p.order = order; p.B = B; p.Tmax = Tmax; p.C = C; p.L = K - 1; p.ldc = ldc;
     Saved s = carve(const_cast<void*>(saved), B, Tmax, C);
-    p.fbeta = s.fbeta; p.fgamma = s.fgamma; p.fdelta = s.fdelta; p.logz2 = s.logz2;
+    p.fbeta = s.fbeta; p.fgamma = s.fgamma; p.fdelta = s.fdelta; p.logz2 = s.logz2; p.fflag = s.fflag;
+    p.trans_succ = trans_succ;
     p.grad = grad_logz; p.d_init = d_init; p.d_trans = d_trans; p.d_len = d_len; p.d_em = d_em;
-    if (!dp_reg_supported(C, p.L, 2)) {
+    if (!dp_reg_supported(C, p.L, 2, trans_succ != nullptr)) {
         set_error("hsmm_logz_backward: shape C=%d K=%d not supported (register-resident DP only)", C, K);
         return HSMM_ERR_SHAPE;
     }

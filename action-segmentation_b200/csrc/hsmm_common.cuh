@@ -94,6 +94,8 @@ struct DpParams {
     const double* offset;  // (B) or null
     const int32_t* lengths;
     const int32_t* order;  // (B) or null
+    const int32_t* trans_pred;  // (C, 4) unmasked predecessors of each class (-1 padded) or null = dense
+    const int32_t* trans_succ;  // (C, 4) unmasked successors of each class (-1 padded) or null = dense
     int B, Tmax, C, L, ldc;
     int W;    // warps per video
     int VPB;  // videos per block
@@ -108,6 +110,7 @@ struct DpParams {
     float* fgamma;  // (B, Tmax+1, ldc)  gamma[n], n = 1..T    (log2 domain)
     float* fdelta;  // (B, Tmax+1)  per-frame normaliser increments delta_n, n = 1..T
     float* logz2;   // (B) log2 Z relative to the accumulated normaliser nu_T
+    float* fflag;   // (B) 1 when the video was recomputed against the dense matrix (sparse hint degenerate)
     double* logz;   // (B)
     // backward
     const float* grad;  // (B)

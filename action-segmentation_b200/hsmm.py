@@ -36,6 +36,26 @@ def ldc_of(C):
     return (C + 3) // 4 * 4
 
 
+SPARSE_WIDTH = 4  # HSMM_SPARSE_WIDTH
+
+
+def sparse_transition_lists(allowed, device):
+    """(pred, succ) int32 (C, 4) device tensors from a boolean [to, from] matrix of NOT-masked
+    transitions, or None when some class has more than 4 unmasked neighbours (-> dense kernels)."""
+    allowed = allowed.cpu()
+    C = allowed.shape[0]
+    if int(allowed.sum(dim=1).max()) > SPARSE_WIDTH or int(allowed.sum(dim=0).max()) > SPARSE_WIDTH:
+        return None
+    pred = torch.full((C, SPARSE_WIDTH), -1, dtype=torch.int32)
+    succ = torch.full((C, SPARSE_WIDTH), -1, dtype=torch.int32)
+    for c in range(C):
+        p = torch.nonzero(allowed[c, :]).flatten()
+        pred[c, :len(p)] = p.to(torch.int32)
+        q = torch.nonzero(allowed[:, c]).flatten()
+        succ[c, :len(q)] = q.to(torch.int32)
+    return pred.to(device).contiguous(), succ.to(device).contiguous()
+
+
 def prepare_lengths(lengths, device):
     """int32 device lengths + processing order (longest first) for load balance."""
     lengths_dev = lengths.to(device=device, dtype=torch.int32).contiguous()
@@ -76,7 +96,7 @@ def emission_scores(features, means, cov_diag, penalty, lengths_i32):
 
 
 def viterbi_decode(em, C, init, trans, lenp, end, offset, lengths_i32, order=None, class_ids=None, want_labels=True,
-                   want_score=True):
+                   want_score=True, trans_pred=None):
     """hsmm_viterbi: returns (spans (B,T+1) int64, labels (B,T) int64 or None, score (B) float64 or None)."""
     _need_cuda(em, init, trans, lenp, end, offset, lengths_i32, order, class_ids)
     lib = _lib.load()
@@ -87,13 +107,13 @@ def viterbi_decode(em, C, init, trans, lenp, end, offset, lengths_i32, order=Non
     spans = torch.empty(B, T + 1, device=em.device, dtype=torch.int64)
     labels = torch.empty(B, T, device=em.device, dtype=torch.int64) if want_labels else None
     score = torch.empty(B, device=em.device, dtype=torch.float64) if want_score else None
-    _lib.check(lib.hsmm_viterbi(_p(em), ldc, _p(init), _p(trans), _p(lenp), _p(end), _p(offset), _p(lengths_i32), _p(order),
-                                _p(class_ids), B, T, C, K, _p(spans), _p(labels), _p(score), _p(ws), _stream()),
-               "hsmm_viterbi")
+    _lib.check(lib.hsmm_viterbi(_p(em), ldc, _p(init), _p(trans), _p(trans_pred), _p(lenp), _p(end), _p(offset),
+                                _p(lengths_i32), _p(order), _p(class_ids), B, T, C, K, _p(spans), _p(labels), _p(score),
+                                _p(ws), _stream()), "hsmm_viterbi")
     return spans, labels, score
 
 
-def logz_forward(em, C, init, trans, lenp, end, offset, lengths_i32, order=None):
+def logz_forward(em, C, init, trans, lenp, end, offset, lengths_i32, order=None, trans_pred=None):
     """hsmm_logz_forward: returns (logz (B) float64, saved workspace)."""
     _need_cuda(em, init, trans, lenp, end, offset, lengths_i32, order)
     lib = _lib.load()
@@ -101,12 +121,13 @@ def logz_forward(em, C, init, trans, lenp, end, offset, lengths_i32, order=None)
     K = lenp.shape[0]
     saved = torch.empty(lib.hsmm_logz_saved_bytes(B, T, C, K), device=em.device, dtype=torch.uint8)
     logz = torch.empty(B, device=em.device, dtype=torch.float64)
-    _lib.check(lib.hsmm_logz_forward(_p(em), ldc, _p(init), _p(trans), _p(lenp), _p(end), _p(offset), _p(lengths_i32),
-                                     _p(order), B, T, C, K, _p(logz), _p(saved), _stream()), "hsmm_logz_forward")
+    _lib.check(lib.hsmm_logz_forward(_p(em), ldc, _p(init), _p(trans), _p(trans_pred), _p(lenp), _p(end), _p(offset),
+                                     _p(lengths_i32), _p(order), B, T, C, K, _p(logz), _p(saved), _stream()),
+               "hsmm_logz_forward")
     return logz, saved
 
 
-def logz_backward(em, C, init, trans, lenp, end, lengths_i32, order, grad_logz, saved, out=None):
+def logz_backward(em, C, init, trans, lenp, end, lengths_i32, order, grad_logz, saved, out=None, trans_succ=None):
     """hsmm_logz_backward: returns (d_init (C), d_trans (C,C), d_len (K,C), d_em (B,T,ldc)).
     `out` may carry pre-allocated (zeroed) d_init/d_trans/d_len views of a packed gradient buffer."""
     lib = _lib.load()
@@ -121,9 +142,9 @@ def logz_backward(em, C, init, trans, lenp, end, lengths_i32, order, grad_logz, 
         d_init, d_trans, d_len = out
     d_em = torch.empty(B, T, ldc, device=dev, dtype=torch.float32)
     g = _f32(grad_logz)
-    _lib.check(lib.hsmm_logz_backward(_p(em), ldc, _p(init), _p(trans), _p(lenp), _p(end), _p(lengths_i32), _p(order), _p(g),
-                                      B, T, C, K, _p(saved), _p(d_init), _p(d_trans), _p(d_len), _p(d_em), _stream()),
-               "hsmm_logz_backward")
+    _lib.check(lib.hsmm_logz_backward(_p(em), ldc, _p(init), _p(trans), _p(trans_succ), _p(lenp), _p(end), _p(lengths_i32),
+                                      _p(order), _p(g), B, T, C, K, _p(saved), _p(d_init), _p(d_trans), _p(d_len), _p(d_em),
+                                      _stream()), "hsmm_logz_backward")
     return d_init, d_trans, d_len, d_em
 
 
@@ -170,13 +191,14 @@ class HsmmLogZ(torch.autograd.Function):
               trans and the length table (the tiny parameter transforms stay in torch autograd)."""
 
     @staticmethod
-    def forward(ctx, features, means, cov_diag, penalty, init, trans, lenp, end, lengths_i32, order):
+    def forward(ctx, features, means, cov_diag, penalty, init, trans, lenp, end, lengths_i32, order, sparse=None):
         C = means.shape[0]
         em, rowterm, offset = emission_scores(features, means, cov_diag, penalty, lengths_i32)
         init_f, trans_f, lenp_f, end_f = _f32(init), _f32(trans), _f32(lenp), _f32(end)
-        logz, saved = logz_forward(em, C, init_f, trans_f, lenp_f, end_f, offset, lengths_i32, order)
+        pred, succ = (None, None) if sparse is None else sparse
+        logz, saved = logz_forward(em, C, init_f, trans_f, lenp_f, end_f, offset, lengths_i32, order, trans_pred=pred)
         ctx.save_for_backward(features, means, cov_diag, em, init_f, trans_f, lenp_f, lengths_i32, saved)
-        ctx.end, ctx.order, ctx.C = end_f, order, C
+        ctx.end, ctx.order, ctx.C, ctx.succ = end_f, order, C, succ
         ctx.mark_non_differentiable(rowterm)
         return logz.to(torch.float32), logz, rowterm
 
@@ -187,13 +209,14 @@ class HsmmLogZ(torch.autograd.Function):
         g = torch.zeros_like(g32) if g32 is None else g32
         if g64 is not None:
             g = g + g64.to(g.dtype)
-        d_init, d_trans, d_len, d_em = logz_backward(em, C, init, trans, lenp, ctx.end, lengths_i32, ctx.order, g, saved)
+        d_init, d_trans, d_len, d_em = logz_backward(em, C, init, trans, lenp, ctx.end, lengths_i32, ctx.order, g, saved,
+                                                     trans_succ=ctx.succ)
         d_means = None
         if ctx.needs_input_grad[1]:
             wx, wsum = weighted_feature_sums(features, d_em, C, lengths_i32)
             d_means = (wx - wsum[:, None] * means) / cov_diag[None, :]
         d_pen = d_em[:, :, :C] if ctx.needs_input_grad[3] else None
-        return None, d_means, None, d_pen, d_init, d_trans, d_len, None, None, None
+        return None, d_means, None, d_pen, d_init, d_trans, d_len, None, None, None, None
 
 
 class HsmmGoldScore(torch.autograd.Function):

@@ -33,10 +33,10 @@ def all_equal(xs):
 class HsmmScores:
     """What `score_features` hands to the DP in place of the dense potential tensor."""
 
-    def __init__(self, em, rowterm, offset, init, trans, lenp, end, lengths_i32, order, C):
+    def __init__(self, em, rowterm, offset, init, trans, lenp, end, lengths_i32, order, C, sparse=None):
         self.em, self.rowterm, self.offset = em, rowterm, offset
         self.init, self.trans, self.lenp, self.end = init, trans, lenp, end
-        self.lengths_i32, self.order, self.C = lengths_i32, order, C
+        self.lengths_i32, self.order, self.C, self.sparse = lengths_i32, order, C, sparse
 
     @property
     def elp(self):
@@ -81,6 +81,7 @@ class SemiMarkovModule(nn.Module):
         self.max_k = args.sm_max_span_length
         self._merge_classes = merge_classes
         self.kl = None
+        self._sparse_cache = {}
 
     @property
     def merge_classes(self):
@@ -286,6 +287,29 @@ class SemiMarkovModule(nn.Module):
             end[b, cols] = 0.0
         return end.to(device)
 
+    def _sparse_hint(self, valid_classes, device):
+        """Unmasked-transition lists for the kernels' sparse mode: with ordering constraints
+        (set_transition_constraints) at most a few entries per class survive the -1e9 mask."""
+        if self.transition_constraints is None:
+            return None
+        key = (None if valid_classes is None else tuple(int(x) for x in valid_classes), str(device))
+        cache = self.__dict__.setdefault('_sparse_cache', {})
+        if key not in cache:
+            allowed = ~self.transition_constraints.detach().cpu()
+            if valid_classes is not None:
+                vc = valid_classes.cpu()
+                allowed = allowed[vc][:, vc]
+            if not self.allow_self_transitions:
+                allowed = allowed & ~torch.eye(allowed.shape[0], dtype=torch.bool)
+            cache[key] = hsmm.sparse_transition_lists(allowed, device)
+        return cache[key]
+
+    def __getstate__(self):
+        d = super().__getstate__() if hasattr(super(), '__getstate__') else dict(self.__dict__)
+        d = dict(d)
+        d['_sparse_cache'] = {}
+        return d
+
     def _scores(self, features, lengths, valid_classes, additional_allowed_ends_per_instance):
         dev = features.device
         if dev.type != 'cuda':
@@ -306,7 +330,8 @@ class SemiMarkovModule(nn.Module):
         end = self._end_scores(valid_classes, features.size(0), additional_allowed_ends_per_instance, dev)
         return dict(means=self.gaussian_means[idx], cov_diag=torch.diagonal(self.gaussian_cov),
                     init=self.initial_log_probs(valid_classes), trans=self.transition_log_probs(valid_classes),
-                    lenp=lenp, end=end, lengths_i32=lengths_i32, order=order, C=C, valid_classes=valid_classes)
+                    lenp=lenp, end=end, lengths_i32=lengths_i32, order=order, C=C, valid_classes=valid_classes,
+                    sparse=self._sparse_hint(valid_classes, dev))
 
     def score_features(self, features, lengths, valid_classes, add_eos, use_mean_z,
                        additional_allowed_ends_per_instance=None, constraints=None, return_elp=False):
@@ -318,7 +343,7 @@ class SemiMarkovModule(nn.Module):
         with torch.no_grad():
             em, rowterm, offset = hsmm.emission_scores(features, s['means'], s['cov_diag'], constraints, s['lengths_i32'])
         scores = HsmmScores(em, rowterm, offset, s['init'].detach(), s['trans'].detach(), s['lenp'].detach(), s['end'],
-                            s['lengths_i32'], s['order'], s['C'])
+                            s['lengths_i32'], s['order'], s['C'], s['sparse'])
         log_det = torch.zeros(features.size(0), device=features.device, requires_grad=False)
         if return_elp:
             return scores, log_det, scores.elp
@@ -344,7 +369,7 @@ class SemiMarkovModule(nn.Module):
                 s['lengths_i32'])
         log_det = torch.zeros(features.size(0), device=features.device, requires_grad=False)
         if spans is None:
-            logz, _, _ = hsmm.HsmmLogZ.apply(*args, s['order'])
+            logz, _, _ = hsmm.HsmmLogZ.apply(*args, s['order'], s['sparse'])
             return logz.mean(), log_det.mean()
         # gold spans arrive in global class ids; map to positions in valid_classes
         dev = features.device
@@ -355,7 +380,7 @@ class SemiMarkovModule(nn.Module):
         local = torch.where(spans >= 0, lut[spans.clamp(min=0)], torch.full_like(spans, -1)).to(torch.int32).contiguous()
         score = hsmm.HsmmGoldScore.apply(*args, local)
         if getattr(self.args, 'sm_train_discriminatively', False):
-            logz, _, _ = hsmm.HsmmLogZ.apply(*args, s['order'])
+            logz, _, _ = hsmm.HsmmLogZ.apply(*args, s['order'], s['sparse'])
             return (score - logz).mean(), log_det.mean()
         return score.mean(), log_det.mean()
 
@@ -378,7 +403,8 @@ class SemiMarkovModule(nn.Module):
                 ids = torch.cat([valid_classes.to(dev), torch.tensor([self.n_classes], device=dev)]).to(torch.int32)
             spans, labels, _ = hsmm.viterbi_decode(scores.em, C, scores.init, scores.trans, scores.lenp, scores.end,
                                                    scores.offset, scores.lengths_i32, scores.order, ids.contiguous(),
-                                                   want_labels=return_labels, want_score=False)
+                                                   want_labels=return_labels, want_score=False,
+                                                   trans_pred=None if scores.sparse is None else scores.sparse[0])
         out = [spans.cpu()]
         if return_elp:
             out.append(scores.elp)

@@ -123,6 +123,8 @@ def make_task(t, steps, V, D, K, tmin, tmax, narration, gen, device):
     tk.lengths_i32, tk.order = hsmm.prepare_lengths(tk.lengths, torch.device(device))
     tk.frames = int(tk.lengths.sum())
     tk.class_ids = torch.arange(C + 1, device=device, dtype=torch.int32)
+    # ordering constraints leave <= 2 unmasked transitions per class: hint for the sparse-transition kernels
+    tk.pred, tk.succ = hsmm.sparse_transition_lists(~tmask, torch.device(device))
     return tk
 
 
@@ -166,16 +168,19 @@ def device_step(tasks, streams, packed, layout, world):
                 o += n
             wx, d_trans, d_len, d_init, wsum, lz = v
             em, rowterm, offset = hsmm.emission_scores(tk.X, tk.means, tk.cov_diag, tk.penalty, tk.lengths_i32)
-            logz, saved = hsmm.logz_forward(em, tk.C, tk.init, tk.trans, tk.lenp, tk.end, offset, tk.lengths_i32, tk.order)
+            logz, saved = hsmm.logz_forward(em, tk.C, tk.init, tk.trans, tk.lenp, tk.end, offset, tk.lengths_i32, tk.order,
+                                            trans_pred=tk.pred)
             g = torch.full((tk.V,), 1.0 / (tk.V * world), device=em.device)
             _, _, _, d_em = hsmm.logz_backward(em, tk.C, tk.init, tk.trans, tk.lenp, tk.end, tk.lengths_i32, tk.order, g,
-                                               saved, out=(d_init, d_trans.view(tk.C, tk.C), d_len.view(tk.K, tk.C)))
+                                               saved, out=(d_init, d_trans.view(tk.C, tk.C), d_len.view(tk.K, tk.C)),
+                                               trans_succ=tk.succ)
             hsmm._lib.check(lib.hsmm_weighted_feature_sums(hsmm._p(tk.X), hsmm._p(d_em), d_em.shape[2], hsmm._p(tk.lengths_i32),
                                                            tk.V, tk.Tmax, tk.D, tk.C, hsmm._p(wx), hsmm._p(wsum),
                                                            hsmm._stream()), "hsmm_weighted_feature_sums")
             lz.copy_(logz.sum().float().reshape(1))
             spans, labels, score = hsmm.viterbi_decode(em, tk.C, tk.init, tk.trans, tk.lenp, tk.end, offset, tk.lengths_i32,
-                                                       tk.order, tk.class_ids, want_labels=True, want_score=False)
+                                                       tk.order, tk.class_ids, want_labels=True, want_score=False,
+                                                       trans_pred=tk.pred)
             outs.append((spans, labels))
     for st in streams:
         ev = torch.cuda.Event()
@@ -249,13 +254,13 @@ def kernel_breakdown(tasks, reps=2):
         for tk in tasks:
             em, rowterm, offset = timed("emission", lambda: hsmm.emission_scores(tk.X, tk.means, tk.cov_diag, tk.penalty, tk.lengths_i32))
             logz, saved = timed("logz_forward", lambda: hsmm.logz_forward(em, tk.C, tk.init, tk.trans, tk.lenp, tk.end, offset,
-                                                                          tk.lengths_i32, tk.order))
+                                                                          tk.lengths_i32, tk.order, trans_pred=tk.pred))
             g = torch.full((tk.V,), 1.0 / tk.V, device=em.device)
             d = timed("logz_backward", lambda: hsmm.logz_backward(em, tk.C, tk.init, tk.trans, tk.lenp, tk.end, tk.lengths_i32,
-                                                                  tk.order, g, saved))
+                                                                  tk.order, g, saved, trans_succ=tk.succ))
             timed("weighted_feature_sums", lambda: hsmm.weighted_feature_sums(tk.X, d[3], tk.C, tk.lengths_i32))
             timed("viterbi", lambda: hsmm.viterbi_decode(em, tk.C, tk.init, tk.trans, tk.lenp, tk.end, offset, tk.lengths_i32,
-                                                         tk.order, tk.class_ids, want_score=False))
+                                                         tk.order, tk.class_ids, want_score=False, trans_pred=tk.pred))
     return {n: acc[n] / reps for n in names}, {n: launches[n] // reps for n in names}
 
 
@@ -484,7 +489,7 @@ def main():
             "config": {"workload": workload_name(args), "frames_per_step_per_gpu": frames, "videos_per_step_per_gpu":
                        sum(tk.V for tk in tasks), "parallelism": "dp%d over videos, 1 packed all-reduce/step" % world,
                        "l2_policy": "inputs larger than L2 (%.1f GB of features per step per GPU)" % (frames * D * 4 / 1e9),
-                       "dp_variants": sorted(set(_lib.dp_variant(tk.C, tk.K, 1) for tk in tasks))},
+                       "dp_variants": sorted(set(_lib.dp_variant(tk.C, tk.K, 1, True) for tk in tasks))},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
         print(json.dumps(out))

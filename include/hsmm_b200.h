@@ -21,7 +21,15 @@
  *   - transition scores are indexed [to, from] (semimarkov_modules.py:153-155, 320-322);
  *   - `end` is the EOS row of the augmented transition matrix (semimarkov_modules.py:462-471):
  *     0 where a class may end the video, -1e9 otherwise; NULL = every class may end;
- *   - `order` (optional) is the processing order of the videos, longest first, for load balance.
+ *   - `order` (optional) is the processing order of the videos, longest first, for load balance;
+ *   - `trans_pred` / `trans_succ` (optional, (C, HSMM_SPARSE_WIDTH) int32, ascending, -1 padded): for every
+ *     class the predecessors (successors) whose transition is NOT masked.  With
+ *     --sm_constrain_transitions (semimarkov.py:41-54, data/crosstask.py:328-388) the matrix is a
+ *     chain with self loops, so <= 2 entries per class survive the -1e9 mask
+ *     (semimarkov_modules.py:298-322); the kernels then visit only the listed entries.  It is a
+ *     hint, not a semantic change: a video whose result is degenerate (<= -1e8, i.e. no path avoids
+ *     the masked transitions) is recomputed against the dense matrix inside the same kernel.
+ *     NULL = dense.
  *
  * Score of a segmentation:
  *   init[c_0] + sum_i (len[l_i, c_i] + sum_{t in seg_i} em[t, c_i]) + sum_{i>=1} trans[c_i, c_{i-1}] + end[c_last]
@@ -40,6 +48,7 @@ extern "C" {
 #define HSMM_ERR_ARG (-1)
 #define HSMM_ERR_SHAPE (-2)
 #define HSMM_ERR_CUDA (-3)
+#define HSMM_SPARSE_WIDTH 4
 
 /* Library version (major*100 + minor) and the last error message of the calling thread. */
 int hsmm_version(void);
@@ -91,9 +100,9 @@ size_t hsmm_logz_saved_bytes(int B, int Tmax, int C, int K);
  * out_score (B) double or NULL: best path score (+ offset).
  * workspace: hsmm_viterbi_workspace_bytes(...) bytes.
  */
-int hsmm_viterbi(const float* em, int ldc, const float* init, const float* trans, const float* lenp,
-                 const float* end, const double* offset, const int32_t* lengths, const int32_t* order,
-                 const int32_t* class_ids, int B, int Tmax, int C, int K,
+int hsmm_viterbi(const float* em, int ldc, const float* init, const float* trans, const int32_t* trans_pred,
+                 const float* lenp, const float* end, const double* offset, const int32_t* lengths,
+                 const int32_t* order, const int32_t* class_ids, int B, int Tmax, int C, int K,
                  int64_t* out_spans, int64_t* out_labels, double* out_score,
                  void* workspace, void* stream);
 
@@ -102,9 +111,10 @@ int hsmm_viterbi(const float* em, int ldc, const float* init, const float* trans
  * (models/semimarkov/semimarkov_modules.py:624,657): out_logz[b] = log sum over segmentations
  * (+ offset[b]).  `saved` (hsmm_logz_saved_bytes) receives what the backward pass needs.
  */
-int hsmm_logz_forward(const float* em, int ldc, const float* init, const float* trans, const float* lenp,
-                      const float* end, const double* offset, const int32_t* lengths, const int32_t* order,
-                      int B, int Tmax, int C, int K, double* out_logz, void* saved, void* stream);
+int hsmm_logz_forward(const float* em, int ldc, const float* init, const float* trans, const int32_t* trans_pred,
+                      const float* lenp, const float* end, const double* offset, const int32_t* lengths,
+                      const int32_t* order, int B, int Tmax, int C, int K, double* out_logz, void* saved,
+                      void* stream);
 
 /*
  * Backward pass / expected counts.  Replaces `loss.backward()` through pytorch-struct and log_hsmm
@@ -115,9 +125,9 @@ int hsmm_logz_forward(const float* em, int ldc, const float* init, const float* 
  * and WRITES d_em (B,Tmax,ldc) = g_b * P(frame t has class c) (0 for t >= lengths[b]).
  * Must follow hsmm_logz_forward with the same inputs and `saved` buffer.
  */
-int hsmm_logz_backward(const float* em, int ldc, const float* init, const float* trans, const float* lenp,
-                       const float* end, const int32_t* lengths, const int32_t* order, const float* grad_logz,
-                       int B, int Tmax, int C, int K, const void* saved,
+int hsmm_logz_backward(const float* em, int ldc, const float* init, const float* trans, const int32_t* trans_succ,
+                       const float* lenp, const float* end, const int32_t* lengths, const int32_t* order,
+                       const float* grad_logz, int B, int Tmax, int C, int K, const void* saved,
                        float* d_init, float* d_trans, float* d_len, float* d_em, void* stream);
 
 /*
@@ -158,7 +168,7 @@ int hsmm_onehot_weights(const int32_t* labels, const int32_t* lengths, int B, in
 
 /* Introspection used by tests/bench: name of the DP kernel variant picked for a shape
  * ("reg<KR,S>/treg", "reg<KR,S>/tsmem", "ring") and how many kernels the library has launched. */
-const char* hsmm_dp_variant(int C, int K, int mode /*0 viterbi, 1 forward, 2 backward*/);
+const char* hsmm_dp_variant(int C, int K, int mode /*0 viterbi, 1 forward, 2 backward*/, int sparse);
 uint64_t hsmm_launch_count(void);
 
 #ifdef __cplusplus

@@ -38,11 +38,20 @@ def rel_err(a, b):
     return float(np.abs(a - b).max() / max(1e-12, np.abs(b).max()))
 
 
-def random_problem(rng, B, Tmax, C, K, Tmin=1, chain=False, ends=False, scale=3.0):
+def random_problem(rng, B, Tmax, C, K, Tmin=1, chain=False, ends=False, scale=3.0, narration=False):
     """Random DP inputs (already in score space): em (B,Tmax,C), init, trans [to,from], lenp (K,C), end."""
     lengths = rng.integers(Tmin, Tmax + 1, size=B)
     lengths[0] = Tmax
     em = rng.normal(size=(B, Tmax, C)) * scale
+    if narration:
+        # soft -1e4 penalty on the odd ("step") classes outside one window each (semimarkov.py:227-232)
+        for b in range(B):
+            for c in range(1, C, 2):
+                lo = int(rng.integers(0, max(1, lengths[b])))
+                hi = lo + int(rng.integers(2, 12))
+                pen = np.full(Tmax, -1e4)
+                pen[lo:hi] = 0.0
+                em[b, :, c] += pen
     em -= em.max(axis=2, keepdims=True)
     init = np.log(rng.dirichlet(np.ones(C)))
     logits = rng.normal(size=(C, C))
@@ -64,6 +73,13 @@ def random_problem(rng, B, Tmax, C, K, Tmin=1, chain=False, ends=False, scale=3.
             if lengths[b] < C:
                 end[b, int(lengths[b]) - 1] = 0.0
     return dict(em=em, lengths=lengths, init=init, trans=trans, lenp=lenp, end=end)
+
+
+def sparse_lists(prob, device="cuda"):
+    """(pred, succ) hint tensors from the unmasked (> -1e8) entries of prob['trans']."""
+    import action_segmentation_b200 as pkg
+    allowed = torch.from_numpy(prob["trans"] > -1e8)
+    return pkg.hsmm.sparse_transition_lists(allowed, torch.device(device))
 
 
 def to_dev(prob, device="cuda"):

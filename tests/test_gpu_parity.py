@@ -5,7 +5,8 @@ import torch
 
 from oracle import hsmm_oracle as O
 from oracle.module_oracle import from_golden, golden_addl_ends
-from tests.helpers import (check_viterbi_against_oracle, module_from_golden, random_problem, rel_err, to_dev)
+from tests.helpers import (check_viterbi_against_oracle, module_from_golden, random_problem, rel_err, sparse_lists,
+                           to_dev)
 
 pytestmark = pytest.mark.gpu
 
@@ -133,10 +134,16 @@ def test_viterbi_random_vs_oracle(shape):
     prob = random_problem(rng, B, Tmax, C, K, Tmin=1, chain=chain, ends=ends)
     prob["lenp"] = O.clamp_len_table(prob["lenp"], Tmax)
     d = to_dev(prob)
+    sp = sparse_lists(prob) if chain else None  # ordering-constrained shapes run the sparse-transition kernels
     spans, labels, score = pkg.hsmm.viterbi_decode(d["em"], C, d["init"], d["trans"], d["lenp"], d["end"], None,
-                                                   d["lengths_i32"], d["order"])
+                                                   d["lengths_i32"], d["order"], trans_pred=None if sp is None else sp[0])
     n_exact = check_viterbi_against_oracle(prob, spans.cpu().numpy(), score.cpu().numpy())
     assert n_exact >= B - 1, "more than one video differs from the oracle path (%d of %d exact)" % (n_exact, B)
+    if chain:  # the hint must not change anything: dense kernels on the same inputs
+        spans_d, _, score_d = pkg.hsmm.viterbi_decode(d["em"], C, d["init"], d["trans"], d["lenp"], d["end"], None,
+                                                      d["lengths_i32"], d["order"])
+        assert (spans_d == spans).all()
+        assert torch.allclose(score_d, score, rtol=1e-6, atol=1e-4)
 
 
 @pytest.mark.parametrize("shape", SHAPES[:7] + SHAPES[10:], ids=lambda s: "B%d_T%d_C%d_K%d" % s[:4])
@@ -145,14 +152,16 @@ def test_logz_and_counts_random_vs_oracle(shape):
     import action_segmentation_b200 as pkg
     B, Tmax, C, K, chain, ends = shape
     rng = np.random.default_rng(200 + C * 7 + K)
-    prob = random_problem(rng, B, Tmax, C, K, Tmin=1, chain=chain, ends=ends)
+    prob = random_problem(rng, B, Tmax, C, K, Tmin=1, chain=chain, ends=ends, narration=chain)
     prob["lenp"] = O.clamp_len_table(prob["lenp"], Tmax)
     d = to_dev(prob)
-    logz, saved = pkg.hsmm.logz_forward(d["em"], C, d["init"], d["trans"], d["lenp"], d["end"], None, d["lengths_i32"], d["order"])
+    sp = sparse_lists(prob) if chain else (None, None)
+    logz, saved = pkg.hsmm.logz_forward(d["em"], C, d["init"], d["trans"], d["lenp"], d["end"], None, d["lengths_i32"],
+                                        d["order"], trans_pred=sp[0])
     w = rng.uniform(0.5, 1.5, size=B)
     g = torch.from_numpy(w).float().cuda()
     d_init, d_trans, d_len, d_em = pkg.hsmm.logz_backward(d["em"], C, d["init"], d["trans"], d["lenp"], d["end"],
-                                                         d["lengths_i32"], d["order"], g, saved)
+                                                         d["lengths_i32"], d["order"], g, saved, trans_succ=sp[1])
     f32 = lambda x: x.astype(np.float32).astype(np.float64)  # noqa: E731
     ref_logz, acc = O.batch_logz_and_counts(f32(prob["em"]), prob["lengths"], f32(prob["init"]), f32(prob["trans"]),
                                             f32(prob["lenp"]), prob["end"], w)
@@ -161,6 +170,47 @@ def test_logz_and_counts_random_vs_oracle(shape):
     assert rel_err(d_trans.cpu().numpy(), acc["E_trans"]) < 1e-4
     assert rel_err(d_len.cpu().numpy(), acc["E_len"]) < 1e-4
     assert rel_err(d_em.cpu().numpy()[:, :, :C], acc["E_em"]) < 1e-4
+
+
+@pytest.mark.parametrize("C,K", [(9, 20), (23, 20), (23, 100)])
+def test_sparse_hint_degenerate_falls_back_to_dense(C, K):
+    """Videos with NO path through the unmasked transitions (chain longer than the video, no extra
+    allowed end): the sparse kernels must notice (result <= -1e8) and reproduce the dense answer, which
+    itself must agree with the oracle on the -1e9-penalised problem."""
+    import action_segmentation_b200 as pkg
+    rng = np.random.default_rng(7 + C + K)
+    B, Tmax = 6, 40
+    prob = random_problem(rng, B, Tmax, C, K, Tmin=20, chain=True, ends=False)
+    prob["lengths"][1] = 3   # cannot reach the last class of the chain: every path pays -1e9
+    prob["lengths"][4] = 5
+    end = np.full((B, C), O.BIG_NEG)
+    end[:, C - 1] = 0.0
+    prob["end"] = end
+    prob["lenp"] = O.clamp_len_table(prob["lenp"], Tmax)
+    d = to_dev(prob)
+    pred, succ = sparse_lists(prob)
+    g = torch.ones(B, device="cuda")
+    outs = []
+    for hint in ((pred, succ), (None, None)):
+        logz, saved = pkg.hsmm.logz_forward(d["em"], C, d["init"], d["trans"], d["lenp"], d["end"], None, d["lengths_i32"],
+                                            d["order"], trans_pred=hint[0])
+        grads = pkg.hsmm.logz_backward(d["em"], C, d["init"], d["trans"], d["lenp"], d["end"], d["lengths_i32"], d["order"],
+                                       g, saved, trans_succ=hint[1])
+        spans, _, score = pkg.hsmm.viterbi_decode(d["em"], C, d["init"], d["trans"], d["lenp"], d["end"], None,
+                                                  d["lengths_i32"], d["order"], trans_pred=hint[0])
+        outs.append((logz, grads, spans, score))
+    (lz_s, gr_s, sp_s, sc_s), (lz_d, gr_d, sp_d, sc_d) = outs
+    assert float(lz_d[1]) < -1e8 and float(lz_d[4]) < -1e8 and float(lz_d[0]) > -1e8
+    assert torch.allclose(lz_s, lz_d, rtol=1e-6)
+    assert torch.allclose(sc_s, sc_d, rtol=1e-6)
+    for b in (0, 2, 3, 5):
+        assert (sp_s[b] == sp_d[b]).all()
+    for a, b_ in zip(gr_s, gr_d):
+        assert torch.allclose(a, b_, rtol=1e-4, atol=1e-5)
+    f32 = lambda x: x.astype(np.float32).astype(np.float64)  # noqa: E731
+    ref_logz, _ = O.batch_logz_and_counts(f32(prob["em"]), prob["lengths"], f32(prob["init"]), f32(prob["trans"]),
+                                          f32(prob["lenp"]), prob["end"])
+    assert np.allclose(lz_d.cpu().numpy(), ref_logz, rtol=1e-6)
 
 
 def test_supervised_fit_golden(golden):

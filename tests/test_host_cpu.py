@@ -38,8 +38,22 @@ def test_variant_table_covers_baseline_shapes():
             [(c, k) for c in (16, 64, 133) for k in (50, 100, 200)]:
         assert pkg._lib.dp_variant(C, K, 0) != "unsupported", (C, K)
     for C, K in [(23, 20), (9, 20), (23, 100), (11, 100)]:
-        assert pkg._lib.dp_variant(C, K, 1) != "unsupported"
-        assert pkg._lib.dp_variant(C, K, 2) != "unsupported"
+        for sparse in (False, True):
+            assert pkg._lib.dp_variant(C, K, 1, sparse) != "unsupported"
+            assert pkg._lib.dp_variant(C, K, 2, sparse) != "unsupported"
+    assert "trans-sparse" in pkg._lib.dp_variant(23, 20, 1, True)
+
+
+def test_sparse_transition_lists():
+    allowed = torch.zeros(5, 5, dtype=torch.bool)
+    for c in range(5):
+        allowed[c, c] = True
+        if c + 1 < 5:
+            allowed[c + 1, c] = True
+    pred, succ = pkg.hsmm.sparse_transition_lists(allowed, torch.device("cpu"))
+    assert pred.tolist() == [[0, -1, -1, -1], [0, 1, -1, -1], [1, 2, -1, -1], [2, 3, -1, -1], [3, 4, -1, -1]]
+    assert succ.tolist() == [[0, 1, -1, -1], [1, 2, -1, -1], [2, 3, -1, -1], [3, 4, -1, -1], [4, -1, -1, -1]]
+    assert pkg.hsmm.sparse_transition_lists(torch.ones(6, 6, dtype=torch.bool), torch.device("cpu")) is None
 
 
 def test_span_utils_golden(golden):
