@@ -39,11 +39,11 @@ def load():
     lib.hsmm_viterbi_workspace_bytes.restype = sz
     lib.hsmm_viterbi_workspace_bytes.argtypes = [i, i, i, i]
     lib.hsmm_logz_saved_bytes.restype = sz
-    lib.hsmm_logz_saved_bytes.argtypes = [i, i, i, i]
+    lib.hsmm_logz_saved_bytes.argtypes = [i, i, i, i, i]
     lib.hsmm_emission.argtypes = [p, p, p, p, f, p, p, i, i, i, i, i, p, p, p, p]
     lib.hsmm_viterbi.argtypes = [p, i, p, p, p, p, p, p, p, p, p, i, i, i, i, p, p, p, p, p]
-    lib.hsmm_logz_forward.argtypes = [p, i, p, p, p, p, p, p, p, p, i, i, i, i, p, p, p]
-    lib.hsmm_logz_backward.argtypes = [p, i, p, p, p, p, p, p, p, p, i, i, i, i, p, p, p, p, p, p]
+    lib.hsmm_logz_forward.argtypes = [p, i, p, p, p, p, p, p, p, p, i, i, i, i, i, p, p, p]
+    lib.hsmm_logz_backward.argtypes = [p, i, p, p, p, p, p, p, p, p, i, i, i, i, i, p, p, p, p, p, p]
     lib.hsmm_weighted_feature_sums.argtypes = [p, p, i, p, i, i, i, i, p, p, p]
     lib.hsmm_gold_score.argtypes = [p, i, p, p, p, p, p, p, p, p, i, i, i, i, p, p, p, p, p, p]
     lib.hsmm_feature_moments.argtypes = [p, p, i, i, i, p, p, p]
@@ -64,5 +64,5 @@ def launch_count():
     return int(load().hsmm_launch_count())
 
 
-def dp_variant(C, K, mode, sparse=False):
-    return load().hsmm_dp_variant(int(C), int(K), int(mode), int(bool(sparse))).decode()
+def dp_variant(C, K, mode, sparse=False, f64_state=False):
+    return load().hsmm_dp_variant(int(C), int(K), int(mode), int(bool(sparse)) | (2 if f64_state else 0)).decode()

@@ -39,8 +39,8 @@ static int num_sms() {
 }
 
 // implemented in the kernel translation units
-bool dp_reg_supported(int C, int L, int mode, bool sparse);
-const char* dp_reg_name(int C, int L, int mode, bool sparse);
+bool dp_reg_supported(int C, int L, int mode, bool sparse, bool xp);
+const char* dp_reg_name(int C, int L, int mode, bool sparse, bool xp);
 int dp_reg_launch(DpParams p, int mode, cudaStream_t st);
 int launch_emission(const float*, const float*, const float*, const float*, float, const float*, const int32_t*, int, int, int,
                     int, int, float*, float*, double*, cudaStream_t);
@@ -71,21 +71,30 @@ static int check_dims(const char* fn, int B, int Tmax, int C, int K, int ldc) {
 }
 
 struct Saved {  // layout of the `saved` buffer of hsmm_logz_forward
-    float* fbeta;
-    float* fgamma;
+    void* fbeta;
+    void* fgamma;
     float* fdelta;
-    float* logz2;
+    double* logz2;
     float* fflag;
 };
 static size_t plane_elems(int B, int Tmax, int C) { return (size_t)B * (Tmax + 1) * (size_t)((C + 3) / 4 * 4); }
-static Saved carve(void* saved, int B, int Tmax, int C) {
+static size_t saved_bytes(int B, int Tmax, int C, bool xp) {
+    const size_t st = xp ? sizeof(double) : sizeof(float);
+    size_t n = 2 * plane_elems(B, Tmax, C) * st + (size_t)B * sizeof(double);  // fbeta, fgamma, logz2
+    n += ((size_t)B * (Tmax + 1) + (size_t)B) * sizeof(float);                  // fdelta, fflag
+    return n + 16;
+}
+static Saved carve(void* saved, int B, int Tmax, int C, bool xp) {
     Saved s;
-    const size_t n = plane_elems(B, Tmax, C);
-    s.fbeta = reinterpret_cast<float*>(saved);
-    s.fgamma = s.fbeta + n;
-    s.fdelta = s.fgamma + n;
-    s.logz2 = s.fdelta + (size_t)B * (Tmax + 1);
-    s.fflag = s.logz2 + B;
+    const size_t st = xp ? sizeof(double) : sizeof(float);
+    const size_t n = plane_elems(B, Tmax, C);  // even (ldc is a multiple of 4): the double planes stay 8-byte aligned
+    char* base = reinterpret_cast<char*>(saved);
+    s.logz2 = reinterpret_cast<double*>(base);
+    base += (size_t)B * sizeof(double);
+    s.fbeta = base;
+    s.fgamma = base + n * st;
+    s.fdelta = reinterpret_cast<float*>(base + 2 * n * st);
+    s.fflag = s.fdelta + (size_t)B * (Tmax + 1);
     return s;
 }
 
@@ -99,9 +108,10 @@ int hsmm_version(void) { return 100; }
 const char* hsmm_last_error(void) { return g_err; }
 uint64_t hsmm_launch_count(void) { return g_launches.load(); }
 
-const char* hsmm_dp_variant(int C, int K, int mode, int sparse) {
+const char* hsmm_dp_variant(int C, int K, int mode, int flags) {
     const int L = K - 1;
-    if (dp_reg_supported(C, L, mode, sparse != 0)) return dp_reg_name(C, L, mode, sparse != 0);
+    const bool sparse = (flags & 1) != 0, xp = (flags & 2) != 0 && mode != 0;
+    if (dp_reg_supported(C, L, mode, sparse, xp)) return dp_reg_name(C, L, mode, sparse, xp);
     return "unsupported";
 }
 
@@ -110,9 +120,9 @@ size_t hsmm_viterbi_workspace_bytes(int B, int Tmax, int C, int K) {
     return plane_elems(B, Tmax, C) * sizeof(uint32_t);
 }
 
-size_t hsmm_logz_saved_bytes(int B, int Tmax, int C, int K) {
+size_t hsmm_logz_saved_bytes(int B, int Tmax, int C, int K, int flags) {
     (void)K;
-    return (2 * plane_elems(B, Tmax, C) + (size_t)B * (Tmax + 1) + 2 * (size_t)B + 4) * sizeof(float);
+    return saved_bytes(B, Tmax, C, (flags & HSMM_FLAG_F64_STATE) != 0);
 }
 
 int hsmm_emission(const float* X, const float* w, const float* bias, const float* inv_var, float row_const,
@@ -154,14 +164,14 @@ int hsmm_viterbi(const float* em, int ldc, const float* init, const float* trans
     p.lengths = lengths; p.order = order; p.B = B; p.Tmax = Tmax; p.C = C; p.L = K - 1; p.ldc = ldc;
     p.bp = reinterpret_cast<uint32_t*>(workspace); p.class_ids = class_ids; p.spans = out_spans; p.labels = out_labels;
     p.score = out_score; p.trans_pred = trans_pred;
-    if (dp_reg_supported(C, p.L, 0, trans_pred != nullptr)) return dp_reg_launch(p, 0, (cudaStream_t)stream);
+    if (dp_reg_supported(C, p.L, 0, trans_pred != nullptr, false)) return dp_reg_launch(p, 0, (cudaStream_t)stream);
     set_error("hsmm_viterbi: shape C=%d K=%d exceeds on-chip capacity", C, K);
     return HSMM_ERR_SHAPE;
 }
 
 int hsmm_logz_forward(const float* em, int ldc, const float* init, const float* trans, const int32_t* trans_pred, const float* lenp,
                       const float* end, const double* offset, const int32_t* lengths, const int32_t* order, int B, int Tmax, int C, int K,
-                      double* out_logz, void* saved, void* stream) {
+                      int flags, double* out_logz, void* saved, void* stream) {
     if (!em || !init || !trans || !lenp || !lengths || !out_logz || !saved) {
         set_error("hsmm_logz_forward: null pointer");
         return HSMM_ERR_ARG;
@@ -176,10 +186,11 @@ int hsmm_logz_forward(const float* em, int ldc, const float* init, const float* 
     memset(&p, 0, sizeof(p));
     p.em = em; p.init = init; p.trans = trans; p.lenp = lenp; p.end = end; p.offset = offset;
     p.lengths = lengths; p.order = order; p.B = B; p.Tmax = Tmax; p.C = C; p.L = K - 1; p.ldc = ldc;
-    Saved s = carve(saved, B, Tmax, C);
+    p.xp = (flags & HSMM_FLAG_F64_STATE) ? 1 : 0;
+    Saved s = carve(saved, B, Tmax, C, p.xp != 0);
     p.fbeta = s.fbeta; p.fgamma = s.fgamma; p.fdelta = s.fdelta; p.logz2 = s.logz2; p.fflag = s.fflag; p.logz = out_logz;
     p.trans_pred = trans_pred;
-    if (!dp_reg_supported(C, p.L, 1, trans_pred != nullptr)) {
+    if (!dp_reg_supported(C, p.L, 1, trans_pred != nullptr, p.xp != 0)) {
         set_error("hsmm_logz_forward: shape C=%d K=%d not supported (register-resident DP only)", C, K);
         return HSMM_ERR_SHAPE;
     }
@@ -188,7 +199,7 @@ int hsmm_logz_forward(const float* em, int ldc, const float* init, const float* 
 
 int hsmm_logz_backward(const float* em, int ldc, const float* init, const float* trans, const int32_t* trans_succ, const float* lenp,
                        const float* end, const int32_t* lengths, const int32_t* order, const float* grad_logz, int B, int Tmax, int C, int K,
-                       const void* saved, float* d_init, float* d_trans, float* d_len, float* d_em, void* stream) {
+                       int flags, const void* saved, float* d_init, float* d_trans, float* d_len, float* d_em, void* stream) {
     if (!em || !init || !trans || !lenp || !lengths || !grad_logz || !saved || !d_init || !d_trans || !d_len || !d_em) {
         set_error("hsmm_logz_backward: null pointer");
         return HSMM_ERR_ARG;
@@ -199,11 +210,12 @@ int hsmm_logz_backward(const float* em, int ldc, const float* init, const float*
     memset(&p, 0, sizeof(p));
     p.em = em; p.init = init; p.trans = trans; p.lenp = lenp; p.end = end;
     p.lengths = lengths; p.order = order; p.B = B; p.Tmax = Tmax; p.C = C; p.L = K - 1; p.ldc = ldc;
-    Saved s = carve(const_cast<void*>(saved), B, Tmax, C);
+    p.xp = (flags & HSMM_FLAG_F64_STATE) ? 1 : 0;
+    Saved s = carve(const_cast<void*>(saved), B, Tmax, C, p.xp != 0);
     p.fbeta = s.fbeta; p.fgamma = s.fgamma; p.fdelta = s.fdelta; p.logz2 = s.logz2; p.fflag = s.fflag;
     p.trans_succ = trans_succ;
     p.grad = grad_logz; p.d_init = d_init; p.d_trans = d_trans; p.d_len = d_len; p.d_em = d_em;
-    if (!dp_reg_supported(C, p.L, 2, trans_succ != nullptr)) {
+    if (!dp_reg_supported(C, p.L, 2, trans_succ != nullptr, p.xp != 0)) {
         set_error("hsmm_logz_backward: shape C=%d K=%d not supported (register-resident DP only)", C, K);
         return HSMM_ERR_SHAPE;
     }

@@ -110,11 +110,7 @@ emission_kernel(const float* __restrict__ X, const float* __restrict__ w, const 
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
                 const int c = cb + 2 * tc + u;
-                if (c < C) {
-                    float v = acc[r][u] + __ldg(bias + c);
-                    if (penalty && fr < nval) v += __ldg(penalty + ((size_t)b * Tmax + t0 + fr) * C + c);
-                    Os[fr * cs + c] = v;
-                }
+                if (c < C) Os[fr * cs + c] = acc[r][u] + __ldg(bias + c);
             }
         }
     }
@@ -126,8 +122,12 @@ emission_kernel(const float* __restrict__ X, const float* __restrict__ w, const 
     // ---- per-frame shift by the best class, 4 threads per frame ------------------------------
     {
         const int fr = tid >> 2, part = tid & 3;
+        // shift = best penalised score; the penalty itself (-1e4 per offending frame, semimarkov.py:25,232)
+        // is added AFTER the shift so that the large number meets an O(1) one exactly once, like the
+        // reference's elp + constraints (semimarkov_modules.py:379-380)
+        const float* pen_r = (penalty && fr < nval) ? penalty + ((size_t)b * Tmax + t0 + fr) * C : nullptr;
         float m = NEG;
-        for (int c = part; c < C; c += 4) m = fmaxf(m, Os[fr * cs + c]);
+        for (int c = part; c < C; c += 4) m = fmaxf(m, Os[fr * cs + c] + (pen_r ? __ldg(pen_r + c) : 0.0f));
         m = fmaxf(m, __shfl_xor_sync(FULL, m, 1));
         m = fmaxf(m, __shfl_xor_sync(FULL, m, 2));
         double contrib = 0.0;
@@ -154,7 +154,12 @@ emission_kernel(const float* __restrict__ X, const float* __restrict__ w, const 
     }
     for (int i = tid; i < nrows * ldc; i += E_THREADS) {
         const int fr = i / ldc, c = i - fr * ldc;
-        em_t[i] = (fr < nval && c < C) ? Os[fr * cs + c] - Rs[fr] : 0.0f;
+        float v = 0.0f;
+        if (fr < nval && c < C) {
+            v = Os[fr * cs + c] - Rs[fr];
+            if (penalty) v += __ldg(penalty + ((size_t)b * Tmax + t0 + fr) * C + c);
+        }
+        em_t[i] = v;
     }
 }
 

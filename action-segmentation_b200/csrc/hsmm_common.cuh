@@ -106,10 +106,11 @@ struct DpParams {
     int64_t* labels;          // (B, Tmax) or null
     double* score;            // (B) or null
     // forward
-    float* fbeta;   // (B, Tmax+1, ldc)  beta[n], n = 0..T-1   (log2 domain)
-    float* fgamma;  // (B, Tmax+1, ldc)  gamma[n], n = 1..T    (log2 domain)
+    int xp;         // 1: per-class state (and fbeta/fgamma) in double -- see state_t in hsmm_dp_reg.cuh
+    void* fbeta;    // (B, Tmax+1, ldc)  beta[n], n = 0..T-1   (log2 domain; float, double when xp)
+    void* fgamma;   // (B, Tmax+1, ldc)  gamma[n], n = 1..T    (log2 domain; float, double when xp)
     float* fdelta;  // (B, Tmax+1)  per-frame normaliser increments delta_n, n = 1..T
-    float* logz2;   // (B) log2 Z relative to the accumulated normaliser nu_T
+    double* logz2;  // (B) log2 Z relative to the accumulated normaliser nu_T
     float* fflag;   // (B) 1 when the video was recomputed against the dense matrix (sparse hint degenerate)
     double* logz;   // (B)
     // backward

@@ -30,9 +30,32 @@
 // underflow.  Base-2 domain, ex2/lg2 on the MUFU pipe.
 //
 // The (B,T,K,C,C) potentials of the reference (semimarkov_modules.py:416-523) are never formed.
+#pragma once
+#include <type_traits>
+
 #include "hsmm_common.cuh"
 
 namespace hsmm {
+
+// Per-class DP state type.  XP ("extended precision") keeps the O(C) per-frame quantities (beta, gamma,
+// eta, zeta, the window reference) in double while the O(C*L) span window stays in float relative to
+// that reference: with -1e4 narration penalties (semimarkov.py:25,227-232) classes whose scores differ
+// by multiples of 1e4 all matter, and a float cannot hold O(1) information next to 1e4-sized offsets.
+template <bool XP>
+using state_t = typename std::conditional<XP, double, float>::type;
+__device__ __forceinline__ float smax(float a, float b) { return fmaxf(a, b); }
+__device__ __forceinline__ double smax(double a, double b) { return fmax(a, b); }
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v = fmax(v, __shfl_xor_sync(FULL, v, off));
+    return v;
+}
+template <int S>
+__device__ __forceinline__ double slice_max(double v) {
+#pragma unroll
+    for (int off = 32 / S; off < 32; off <<= 1) v = fmax(v, __shfl_xor_sync(FULL, v, off));
+    return v;
+}
 
 constexpr int F = 4;    // frames per register prefetch chunk
 constexpr int SPW = 4;  // sparse transition list width (HSMM_SPARSE_WIDTH)
@@ -55,11 +78,13 @@ __host__ __device__ inline int ld_trans(int W, int S) {
 // ---------------------------------------------------------------------------------------------
 // forward: Viterbi (VIT) or log-partition (FWD)
 // ---------------------------------------------------------------------------------------------
-template <bool VIT, int KR, int S, int TM, bool LREG, int MAXT>
+template <bool VIT, bool XP, int KR, int S, int TM, bool LREG, int MAXT>
 __global__ void __launch_bounds__(MAXT) dp_forward_kernel(const DpParams p) {
+    static_assert(!(VIT && XP), "extended-precision state is a log-semiring option");
+    using ST = state_t<XP>;
     constexpr int CPW = Lay<S>::CPW;
     constexpr int CRR = Lay<S>::CRR;
-    extern __shared__ float smem[];
+    extern __shared__ __align__(16) float smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int W = p.W, C = p.C, L = p.L, ldc = p.ldc, Tmax = p.Tmax;
     const int G = W * 32;
@@ -69,13 +94,15 @@ __global__ void __launch_bounds__(MAXT) dp_forward_kernel(const DpParams p) {
     const int ldT = ld_trans(W, S);
     const float SC = VIT ? 1.0f : LOG2E;
 
-    // shared layout: [transT C*ldT (TM==1)] [len columns KR*G (!LREG)] [per group: gamma 2*cpad, warp maxima 2*W]
+    // shared layout: [transT C*ldT (TM==1)] [len columns KR*G (!LREG)] [per group: gamma 2*cpad (ST), warp maxima 2*W]
     float* transT = smem;
     float* lens = smem + (TM == 1 ? C * ldT : 0);
     float* gbase = lens + (LREG ? 0 : KR * G);
-    const int per_group = 2 * cpad + 2 * W;
-    float* gam_s = gbase + slot * per_group;
-    float* wmax_s = gam_s + 2 * cpad;
+    gbase += (XP ? ((gbase - smem) & 1) : 0);  // 8-byte alignment of the double gamma rows
+    constexpr int STW = sizeof(ST) / sizeof(float);
+    const int per_group = 2 * cpad * STW + 2 * W;
+    ST* gam_s = reinterpret_cast<ST*>(gbase + slot * per_group);
+    float* wmax_s = gbase + slot * per_group + 2 * cpad * STW;
 
     const int cl = lane % CPW, j = lane / CPW;
     const int c = wig * CPW + cl;
@@ -161,10 +188,12 @@ __global__ void __launch_bounds__(MAXT) dp_forward_kernel(const DpParams p) {
 
     const float* em_b = p.em + (size_t)b * Tmax * ldc;
     const size_t row0 = (size_t)b * (Tmax + 1);
-    if (!VIT && owner) p.fbeta[row0 * ldc + c] = init_c;
+    ST* const fbeta = reinterpret_cast<ST*>(p.fbeta);
+    ST* const fgamma = reinterpret_cast<ST*>(p.fgamma);
+    if (!VIT && owner) fbeta[row0 * ldc + c] = init_c;
 
     bool dense_pass = (TM != 2);  // TM == 2: first pass sparse, second (rare) pass dense from global memory
-    float final_v = 0.0f;         // VIT: best score; FWD: log2 Z; both relative to nu_T
+    ST final_v = 0;               // VIT: best score; FWD: log2 Z; both relative to nu_T
     int final_c = 0;
     double nu = 0.0;
 
@@ -173,10 +202,11 @@ __global__ void __launch_bounds__(MAXT) dp_forward_kernel(const DpParams p) {
         float A[KR];
 #pragma unroll
         for (int i = 0; i < KR; ++i) A[i] = NEG;
-        float beta = init_c;  // beta^[n-1][c], relative to nu_n
-        float gprev = NEG;    // gamma~[n-1][c], relative to nu_{n-1}
-        float rref = 0.0f;    // FWD: reference the window is stored against
-        float gmprev = 0.0f;  // gm_{n-1}
+        ST beta = init_c;   // beta^[n-1][c], relative to nu_n
+        ST gprev = NEG;     // gamma~[n-1][c], relative to nu_{n-1}
+        ST rref = 0;        // FWD: rho_{n-1}; the window is stored against r_{n-1} = e_{n-1} + rho_{n-1}
+        ST eprev = 0;       // FWD: e_{n-1}
+        float gmprev = 0.0f;  // gm_{n-1} (a float by construction, also in XP: it is only a normaliser)
         nu = 0.0;
         const bool use_smem = (TM != 2) || dense_pass || W > 1;
 
@@ -197,9 +227,9 @@ __global__ void __launch_bounds__(MAXT) dp_forward_kernel(const DpParams p) {
             for (int f = 0; f < F; ++f) {
                 const int n = n0 + f;
                 if (n > T) break;
-                const float e = ecur[f] * SC;
+                const ST e = (ST)ecur[f] * (ST)SC;
                 nu += (double)gmprev;
-                float gamma;
+                ST gamma;
                 int bk = 0;
                 // ---- phase 1 -----------------------------------------------------------------
                 if constexpr (VIT) {
@@ -235,15 +265,19 @@ __global__ void __launch_bounds__(MAXT) dp_forward_kernel(const DpParams p) {
                     slice_argmax<S>(b0, bk);
                     gamma = valid ? b0 : NEG;
                 } else {
-                    // every term <= rnew; the window is stored relative to that reference
-                    const float rnew = fmaxf(gprev - gmprev + e + maxstep, beta + e + ln_first);
-                    const float eo = e - gmprev + (rref - rnew);
+                    // every term <= r_n = e + rho; the window is stored relative to that reference.  The
+                    // (possibly huge: -1e4 narration penalty, -1e9 masks) emission never meets an O(1)
+                    // number before it has cancelled: the shift of the old slots is
+                    // r_{n-1} - gm_{n-1} - rho_n = (e_{n-1} - rho_n) + (rho_{n-1} - gm_{n-1}).
+                    const ST rho = smax(gprev - (ST)gmprev + (ST)maxstep, beta + (ST)ln_first);
+                    const float eo = (float)((eprev - rho) + (rref - (ST)gmprev));
                     float carry = 0.0f;
                     if (S > 1) carry = __shfl_up_sync(FULL, A[KR - 1], CPW);
 #pragma unroll
                     for (int i = KR - 1; i > 0; --i) A[i] = A[i - 1] + eo;
-                    A[0] = (j == 0) ? (beta + e) - rnew : carry + eo;
-                    rref = rnew;
+                    A[0] = (j == 0) ? (float)(beta - rho) : carry + eo;
+                    rref = rho;
+                    eprev = e;
                     float sp[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
                     for (int i = 0; i < KR; ++i) sp[i & 3] += ex2(A[i] + LN(i));
@@ -265,22 +299,22 @@ __global__ void __launch_bounds__(MAXT) dp_forward_kernel(const DpParams p) {
                             mfix = m;
                         }
                     }
-                    gamma = valid ? rnew + mfix + lg2(s) : NEG;
+                    gamma = valid ? (e + rho) + (ST)(mfix + lg2(s)) : (ST)NEG;
                 }
                 gprev = gamma;
                 // ---- group maximum of gamma: the normaliser increment ----------------------------
-                float gm = warp_max(owner ? gamma : NEG);
-                float* gs = gam_s + (n & 1) * cpad;
+                float gm = warp_max(owner ? (float)gamma : NEG);
+                ST* gs = gam_s + (n & 1) * cpad;
                 if (W > 1 && lane == 0) wmax_s[(n & 1) * W + wig] = gm;
                 if (use_smem) {
-                    if (j == 0) gs[wig * CPW + cl] = valid ? gamma : NEG;
+                    if (j == 0) gs[wig * CPW + cl] = valid ? gamma : (ST)NEG;
                     group_sync(W, bar_id);
                 }
                 if (W > 1) {
                     gm = NEG;
                     for (int q = 0; q < W; ++q) gm = fmaxf(gm, wmax_s[(n & 1) * W + q]);
                 }
-                if (!VIT && owner) p.fgamma[(row0 + n) * ldc + c] = gamma;
+                if (!VIT && owner) fgamma[(row0 + n) * ldc + c] = gamma;
                 if (n == T) {
                     if (VIT && owner) p.bp[(row0 + n) * ldc + c] = (uint32_t)bk << 16;
                     break;
@@ -295,7 +329,7 @@ __global__ void __launch_bounds__(MAXT) dp_forward_kernel(const DpParams p) {
                         if constexpr (TM == 2) {
 #pragma unroll
                             for (int q = 0; q < SPW; ++q) {
-                                const float gv = (W == 1) ? __shfl_sync(FULL, gamma, pidx[q]) : gs[pidx[q]];
+                                const float gv = (W == 1) ? __shfl_sync(FULL, (float)gamma, pidx[q]) : (float)gs[pidx[q]];
                                 const float v = gv + pval[q];
                                 if (v > best || q == 0) {
                                     best = v;
@@ -306,7 +340,7 @@ __global__ void __launch_bounds__(MAXT) dp_forward_kernel(const DpParams p) {
                     } else if constexpr (TM == 0) {
 #pragma unroll
                         for (int i = 0; i < CRR; ++i) {
-                            const float v = gs[j * CRR + i] + tr[i];  // padding: gs = NEG, tr = NEG
+                            const float v = (float)gs[j * CRR + i] + tr[i];  // padding: gs = NEG, tr = NEG
                             if (v > best || i == 0) {
                                 best = v;
                                 bc = j * CRR + i;
@@ -316,7 +350,7 @@ __global__ void __launch_bounds__(MAXT) dp_forward_kernel(const DpParams p) {
                     } else if constexpr (TM == 1) {
                         bc = j;
                         for (int c1 = j; c1 < C; c1 += S) {
-                            const float v = gs[c1] + transT[c1 * ldT + c];
+                            const float v = (float)gs[c1] + transT[c1 * ldT + c];
                             if (v > best || c1 == j) {
                                 best = v;
                                 bc = c1;
@@ -326,7 +360,7 @@ __global__ void __launch_bounds__(MAXT) dp_forward_kernel(const DpParams p) {
                     } else {  // TM == 2, dense fallback straight from global memory (rare)
                         bc = j;
                         for (int c1 = j; c1 < C; c1 += S) {
-                            const float v = gs[c1] + (valid ? __ldg(p.trans + (size_t)c * C + c1) : NEG);
+                            const float v = (float)gs[c1] + (valid ? __ldg(p.trans + (size_t)c * C + c1) : NEG);
                             if (v > best || c1 == j) {
                                 best = v;
                                 bc = c1;
@@ -339,18 +373,18 @@ __global__ void __launch_bounds__(MAXT) dp_forward_kernel(const DpParams p) {
                 } else {
                     if (TM == 2 && !dense_pass) {
                         if constexpr (TM == 2) {
-                            float v[SPW];
-                            float m = NEG;
+                            ST v[SPW];
+                            ST m = NEG;
 #pragma unroll
                             for (int q = 0; q < SPW; ++q) {
-                                const float gv = (W == 1) ? __shfl_sync(FULL, gamma, pidx[q]) : gs[pidx[q]];
-                                v[q] = gv + pval[q];
-                                m = fmaxf(m, v[q]);
+                                const ST gv = (W == 1) ? __shfl_sync(FULL, gamma, pidx[q]) : gs[pidx[q]];
+                                v[q] = gv + (ST)pval[q];
+                                m = smax(m, v[q]);
                             }
                             float s = 0.0f;
 #pragma unroll
-                            for (int q = 0; q < SPW; ++q) s += ex2(v[q] - m);
-                            beta = valid ? (m - gm) + lg2(s) : NEG;
+                            for (int q = 0; q < SPW; ++q) s += ex2((float)(v[q] - m));
+                            beta = valid ? (m - (ST)gm) + (ST)lg2(s) : (ST)NEG;
                         }
                     } else {
                         // single pass against the bound gm + trmax; exact two-pass when it underflows
@@ -358,32 +392,32 @@ __global__ void __launch_bounds__(MAXT) dp_forward_kernel(const DpParams p) {
                         if constexpr (TM == 0) {
                             float sp[2] = {0.0f, 0.0f};
 #pragma unroll
-                            for (int i = 0; i < CRR; ++i) sp[i & 1] += ex2((gs[j * CRR + i] - gm) + tr[i]);
+                            for (int i = 0; i < CRR; ++i) sp[i & 1] += ex2((float)(gs[j * CRR + i] - (ST)gm) + tr[i]);
                             s = sp[0] + sp[1];
                         } else if constexpr (TM == 1) {
-                            const float off = gm + trmax;
-                            for (int c1 = j; c1 < C; c1 += S) s += ex2(gs[c1] + transT[c1 * ldT + c] - off);
+                            const float off = trmax;
+                            for (int c1 = j; c1 < C; c1 += S) s += ex2((float)(gs[c1] - (ST)gm) + (transT[c1 * ldT + c] - off));
                         }
                         s = slice_sum<S>(s);
-                        float mfix = 0.0f;
+                        ST mfix = 0;
                         const bool bad = (TM == 2) || (valid && !(s > TINY));
                         if (__any_sync(FULL, bad)) {
-                            float m = NEG;
+                            ST m = NEG;
                             for (int c1 = j; c1 < C; c1 += S)
-                                m = fmaxf(m, gs[c1] + (valid ? __ldg(p.trans + (size_t)c * C + c1) * SC : NEG));
+                                m = smax(m, gs[c1] + (ST)(valid ? __ldg(p.trans + (size_t)c * C + c1) * SC : NEG));
                             m = slice_max<S>(m);
                             float s2p = 0.0f;
                             for (int c1 = j; c1 < C; c1 += S)
-                                s2p += ex2(gs[c1] + (valid ? __ldg(p.trans + (size_t)c * C + c1) * SC : NEG) - m);
+                                s2p += ex2((float)(gs[c1] + (ST)(valid ? __ldg(p.trans + (size_t)c * C + c1) * SC : NEG) - m));
                             s2p = slice_sum<S>(s2p);
                             if (bad) {
                                 s = s2p;
-                                mfix = m - gm - trmax;
+                                mfix = (m - (ST)gm) - (ST)trmax;
                             }
                         }
-                        beta = valid ? trmax + mfix + lg2(s) : NEG;
+                        beta = valid ? ((ST)trmax + mfix) + (ST)lg2(s) : (ST)NEG;
                     }
-                    if (owner) p.fbeta[(row0 + n) * ldc + c] = beta;
+                    if (owner) fbeta[(row0 + n) * ldc + c] = beta;
                 }
             }
         }
@@ -391,24 +425,24 @@ __global__ void __launch_bounds__(MAXT) dp_forward_kernel(const DpParams p) {
         // ---- termination -------------------------------------------------------------------
         // gamma~[T] sits in gam_s (dense / multi-warp) or only in registers (sparse, one warp): put it
         // in shared memory in every case so that one code path finishes the video.
-        float* gT = gam_s + (T & 1) * cpad;
+        ST* gT = gam_s + (T & 1) * cpad;
         if (!use_smem) {
-            if (j == 0) gT[wig * CPW + cl] = valid ? gprev : NEG;
+            if (j == 0) gT[wig * CPW + cl] = valid ? gprev : (ST)NEG;
             group_sync(W, bar_id);
         }
         if constexpr (!VIT) {
-            float m = NEG;
-            for (int cc = lane; cc < C; cc += 32) m = fmaxf(m, gT[cc] + (endb ? endb[cc] * SC : 0.0f));
+            ST m = NEG;
+            for (int cc = lane; cc < C; cc += 32) m = smax(m, gT[cc] + (ST)(endb ? endb[cc] * SC : 0.0f));
             m = warp_max(m);
             float s = 0.0f;
-            for (int cc = lane; cc < C; cc += 32) s += ex2(gT[cc] + (endb ? endb[cc] * SC : 0.0f) - m);
+            for (int cc = lane; cc < C; cc += 32) s += ex2((float)(gT[cc] + (ST)(endb ? endb[cc] * SC : 0.0f) - m));
             s = warp_sum(s);
-            final_v = m + lg2(s);
+            final_v = m + (ST)lg2(s);
         } else {
             float best = NEG;
             int bc = 0x7fffffff;
             for (int cc = lane; cc < C; cc += 32) {
-                const float v = gT[cc] + (endb ? endb[cc] : 0.0f);
+                const float v = (float)gT[cc] + (endb ? endb[cc] : 0.0f);
                 if (v > best || bc == 0x7fffffff) {
                     best = v;
                     bc = cc;
@@ -436,7 +470,7 @@ __global__ void __launch_bounds__(MAXT) dp_forward_kernel(const DpParams p) {
 
     if constexpr (!VIT) {
         if (gtid == 0) {
-            p.logz2[b] = final_v;
+            p.logz2[b] = (double)final_v;
             p.fflag[b] = (TM == 2 && dense_pass) ? 1.0f : 0.0f;
             p.logz[b] = (nu + (double)final_v) * LN2 + (p.offset ? p.offset[b] : 0.0);
         }
@@ -475,11 +509,12 @@ __global__ void __launch_bounds__(MAXT) dp_forward_kernel(const DpParams p) {
 // ---------------------------------------------------------------------------------------------
 // backward: expected counts
 // ---------------------------------------------------------------------------------------------
-template <int KR, int S, int TM, bool LREG, int MAXT>
+template <bool XP, int KR, int S, int TM, bool LREG, int MAXT>
 __global__ void __launch_bounds__(MAXT) dp_backward_kernel(const DpParams p) {
+    using ST = state_t<XP>;
     constexpr int CPW = Lay<S>::CPW;
     constexpr int CRR = Lay<S>::CRR;
-    extern __shared__ float smem[];
+    extern __shared__ __align__(16) float smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int W = p.W, C = p.C, L = p.L, ldc = p.ldc, Tmax = p.Tmax;
     const int G = W * 32;
@@ -489,13 +524,15 @@ __global__ void __launch_bounds__(MAXT) dp_backward_kernel(const DpParams p) {
     const int ldT = ld_trans(W, S);
     const float SC = LOG2E;
 
-    // shared: [trans C*ldT (TM==1)] [len columns KR*G (!LREG)] [per group: zeta 2*cpad, Etr C*ldT (TM != 0)]
+    // shared: [trans C*ldT (TM==1)] [len columns KR*G (!LREG)] [per group: zeta 2*cpad (ST), Etr C*ldT (TM != 0)]
     float* trans_s = smem;
     float* lens = smem + (TM == 1 ? C * ldT : 0);
     float* gbase = lens + (LREG ? 0 : KR * G);
-    const int per_group = 2 * cpad + (TM == 0 ? 0 : C * ldT);
-    float* zet_s = gbase + slot * per_group;
-    float* etr_s = zet_s + 2 * cpad;  // TM == 1 always, TM == 2 only in the dense fallback
+    gbase += (XP ? ((gbase - smem) & 1) : 0);
+    constexpr int STW = sizeof(ST) / sizeof(float);
+    const int per_group = 2 * cpad * STW + (TM == 0 ? 0 : C * ldT + (XP ? ((C * ldT) & 1) : 0));
+    ST* zet_s = reinterpret_cast<ST*>(gbase + slot * per_group);
+    float* etr_s = gbase + slot * per_group + 2 * cpad * STW;  // TM == 1 always, TM == 2 only in the dense fallback
 
     const int cl = lane % CPW, j = lane / CPW;
     const int c = wig * CPW + cl;
@@ -510,7 +547,7 @@ __global__ void __launch_bounds__(MAXT) dp_backward_kernel(const DpParams p) {
     }
     if constexpr (TM != 0) {
         for (int g = 0; g < p.VPB; ++g) {
-            float* e = gbase + g * per_group + 2 * cpad;
+            float* e = gbase + g * per_group + 2 * cpad * STW;
             for (int i = threadIdx.x; i < C * ldT; i += blockDim.x) e[i] = 0.0f;
         }
     }
@@ -577,42 +614,44 @@ __global__ void __launch_bounds__(MAXT) dp_backward_kernel(const DpParams p) {
         }
     }
     const float endc = valid ? (p.end ? p.end[(size_t)b * C + c] : 0.0f) * SC : NEG;
-    const float lzrel = p.logz2[b];  // log2 Z relative to nu_T
+    const ST lzrel = (ST)p.logz2[b];  // log2 Z relative to nu_T
     const float w = p.grad[b];
     const float init_c = valid ? p.init[c] * SC : NEG;
 
     const float* em_b = p.em + (size_t)b * Tmax * ldc;
     const size_t row0 = (size_t)b * (Tmax + 1);
-    const float* fb = p.fbeta + row0 * ldc;
-    const float* fg = p.fgamma + row0 * ldc;
+    const ST* fb = reinterpret_cast<const ST*>(p.fbeta) + row0 * ldc;
+    const ST* fg = reinterpret_cast<const ST*>(p.fgamma) + row0 * ldc;
     const float* fd = p.fdelta + row0;
     float* dem = p.d_em + (size_t)b * Tmax * ldc;
 
     // Frame n: zeta^[n] = zeta[n] - mu_{n+1}, eta~[n] = eta[n] - mu_n with mu_n = logZ - nu_n, so that
     // posteriors are exp(forward + backward) of O(1) numbers:
     //   S[n,c] = exp(beta^[n][c] + zeta^[n][c]),  F[n,c] = exp(gamma~[n][c] + eta~[n][c]).
-    float eta = valid ? endc - lzrel : NEG;  // eta~[T]
-    float zprev = NEG;                       // zeta^[n+1][c]
-    float rref = 0.0f;
-    float occ = 0.0f, comp = 0.0f;  // Kahan-compensated occupancy
-    float Fprev = valid ? w * ex2(__ldg(fg + (size_t)T * ldc + c) + endc - lzrel) : 0.0f;
+    ST eta = valid ? (ST)endc - lzrel : (ST)NEG;  // eta~[T]
+    ST zprev = NEG;                               // zeta^[n+1][c]
+    ST rref = 0, eprev = 0;                       // rho_{n+1}, e_{n+1}
+    float occ = 0.0f, comp = 0.0f;                // Kahan-compensated occupancy
+    float Fprev = valid ? w * ex2((float)(__ldg(fg + (size_t)T * ldc + c) + (ST)endc - lzrel)) : 0.0f;
     float Sprev = 0.0f;
     float gm_next = 0.0f;  // gm_{n+1}
 
     for (int i = T * ldc + gtid; i < Tmax * ldc; i += G) dem[i] = 0.0f;  // frames beyond the video
 
-    float enext[F], bnext[F], gnext[F], dnext[F];
+    float enext[F], dnext[F];
+    ST bnext[F], gnext[F];
 #pragma unroll
     for (int f = 0; f < F; ++f) {
         const int n = T - 1 - f;
         const bool ok = valid && n >= 0;
         dnext[f] = (n >= 1) ? __ldg(fd + n) : 0.0f;  // gm_n
         enext[f] = ok ? __ldg(em_b + (size_t)n * ldc + c) : 0.0f;
-        bnext[f] = (ok && n > 0) ? __ldg(fb + (size_t)n * ldc + c) : 0.0f;
-        gnext[f] = (ok && n > 0) ? __ldg(fg + (size_t)n * ldc + c) : 0.0f;
+        bnext[f] = (ok && n > 0) ? __ldg(fb + (size_t)n * ldc + c) : (ST)0;
+        gnext[f] = (ok && n > 0) ? __ldg(fg + (size_t)n * ldc + c) : (ST)0;
     }
     for (int n0 = T - 1; n0 >= 0; n0 -= F) {
-        float ecur[F], bcur[F], gcur[F], dcur[F];
+        float ecur[F], dcur[F];
+        ST bcur[F], gcur[F];
 #pragma unroll
         for (int f = 0; f < F; ++f) {
             ecur[f] = enext[f];
@@ -626,26 +665,31 @@ __global__ void __launch_bounds__(MAXT) dp_backward_kernel(const DpParams p) {
             const bool ok = valid && n >= 0;
             dnext[f] = (n >= 1) ? __ldg(fd + n) : 0.0f;
             enext[f] = ok ? __ldg(em_b + (size_t)n * ldc + c) : 0.0f;
-            bnext[f] = (ok && n > 0) ? __ldg(fb + (size_t)n * ldc + c) : 0.0f;
-            gnext[f] = (ok && n > 0) ? __ldg(fg + (size_t)n * ldc + c) : 0.0f;
+            bnext[f] = (ok && n > 0) ? __ldg(fb + (size_t)n * ldc + c) : (ST)0;
+            gnext[f] = (ok && n > 0) ? __ldg(fg + (size_t)n * ldc + c) : (ST)0;
         }
 #pragma unroll
         for (int f = 0; f < F; ++f) {
             const int n = n0 - f;
             if (n < 0) break;
-            const float e = ecur[f] * SC;
+            const ST e = (ST)ecur[f] * (ST)SC;
             // ---- phase 1: zeta^[n][c] (single pass against the bound r) and length counts ---------
-            const float rnew = fmaxf(zprev - gm_next + e + maxstep, eta + e + ln_first);
-            const float eo = e - gm_next + (rref - rnew);
+            // window relative to r_n = e_n + rho_n; large emissions cancel before they meet O(1) numbers
+            // (see dp_forward_kernel): shift of the old slots = (e_{n+1} - rho_n) + (rho_{n+1} - gm_{n+1}).
+            const ST rho = smax(zprev - (ST)gm_next + (ST)maxstep, eta + (ST)ln_first);
+            const float eo = (float)((eprev - rho) + (rref - (ST)gm_next));
             float carry = 0.0f;
             if (S > 1) carry = __shfl_up_sync(FULL, Bq[KR - 1], CPW);
 #pragma unroll
             for (int i = KR - 1; i > 0; --i) Bq[i] = Bq[i - 1] + eo;
-            Bq[0] = (j == 0) ? (eta + e) - rnew : carry + eo;
-            rref = rnew;
-            const float betan = (n == 0) ? init_c : bcur[f];
-            // exponent clamped: when it would overflow the class has (s <= TINY) and is redone below
-            const float coef0 = valid ? w * ex2(fminf(betan + rnew, 100.0f)) : 0.0f;
+            Bq[0] = (j == 0) ? (float)(eta - rho) : carry + eo;
+            rref = rho;
+            eprev = e;
+            const ST betan = (n == 0) ? (ST)init_c : bcur[f];
+            // forward + backward exponent: three numbers of which two may be huge and cancel -> summed in
+            // double.  Clamped: when it would overflow the class has (s <= TINY) and is redone below.
+            const double fb2 = (double)betan + (double)e + (double)rho;
+            const float coef0 = valid ? w * ex2(fminf((float)fb2, 100.0f)) : 0.0f;
             float sp[2] = {0.0f, 0.0f};
 #pragma unroll
             for (int i = 0; i < KR; ++i) {
@@ -662,7 +706,7 @@ __global__ void __launch_bounds__(MAXT) dp_backward_kernel(const DpParams p) {
 #pragma unroll
                 for (int i = 1; i < KR; ++i) m = fmaxf(m, Bq[i] + LN(i));
                 m = slice_max<S>(m);
-                const float coefx = valid ? w * ex2(betan + rnew + m) : 0.0f;
+                const float coefx = valid ? w * ex2((float)(fb2 + (double)m)) : 0.0f;
                 float s2p = 0.0f;
 #pragma unroll
                 for (int i = 0; i < KR; ++i) {
@@ -678,7 +722,7 @@ __global__ void __launch_bounds__(MAXT) dp_backward_kernel(const DpParams p) {
                     coef = coefx;
                 }
             }
-            const float zeta = valid ? rnew + mfix + lg2(s) : NEG;
+            const ST zeta = valid ? (e + rho) + (ST)(mfix + lg2(s)) : (ST)NEG;
             const float Sc = coef * s;
             zprev = zeta;
             // ---- occupancy of frame n ---------------------------------------------------------
@@ -696,69 +740,70 @@ __global__ void __launch_bounds__(MAXT) dp_backward_kernel(const DpParams p) {
             }
             const float gm_n = dcur[f];
             // ---- phase 2: eta~[n][c1] = (+)_c2 trans[c2,c1] + zeta^[n][c2] - gm_n; transition counts --
-            float* zs = zet_s + (n & 1) * cpad;
+            ST* zs = zet_s + (n & 1) * cpad;
             if (use_smem) {
-                if (j == 0) zs[wig * CPW + cl] = valid ? zeta : NEG;
+                if (j == 0) zs[wig * CPW + cl] = valid ? zeta : (ST)NEG;
                 group_sync(W, bar_id);
             }
-            const float gam = gcur[f];
+            const ST gam = gcur[f];
             if (TM == 2 && !dense_pass) {
                 if constexpr (TM == 2) {
-                    float v[SPW];
-                    float m2 = NEG;
+                    ST v[SPW];
+                    ST m2 = NEG;
 #pragma unroll
                     for (int q = 0; q < SPW; ++q) {
-                        const float zv = (W == 1) ? __shfl_sync(FULL, zeta, sidx[q]) : zs[sidx[q]];
-                        v[q] = zv + sval[q];
-                        m2 = fmaxf(m2, v[q]);
+                        const ST zv = (W == 1) ? __shfl_sync(FULL, zeta, sidx[q]) : zs[sidx[q]];
+                        v[q] = zv + (ST)sval[q];
+                        m2 = smax(m2, v[q]);
                     }
-                    const float coef2 = valid ? w * ex2(gam + m2 - gm_n) : 0.0f;
+                    const float coef2 = valid ? w * ex2((float)((gam + m2) - (ST)gm_n)) : 0.0f;
                     float s2 = 0.0f;
 #pragma unroll
                     for (int q = 0; q < SPW; ++q) {
-                        const float pq = ex2(v[q] - m2);
+                        const float pq = ex2((float)(v[q] - m2));
                         s2 += pq;
                         Es[q] = fmaf(pq, coef2, Es[q]);
                     }
-                    eta = valid ? (m2 - gm_n) + lg2(s2) : NEG;
+                    eta = valid ? (m2 - (ST)gm_n) + (ST)lg2(s2) : (ST)NEG;
                     Fprev = coef2 * s2;
                 }
             } else {
-                float m2 = NEG;
+                ST m2 = NEG;
                 if constexpr (TM == 0) {
 #pragma unroll
-                    for (int i = 0; i < CRR; ++i) m2 = fmaxf(m2, zs[j * CRR + i] + tr[i]);
+                    for (int i = 0; i < CRR; ++i) m2 = smax(m2, zs[j * CRR + i] + (ST)tr[i]);
                 } else if constexpr (TM == 1) {
-                    for (int c2 = j; c2 < C; c2 += S) m2 = fmaxf(m2, zs[c2] + trans_s[c2 * ldT + c]);
+                    for (int c2 = j; c2 < C; c2 += S) m2 = smax(m2, zs[c2] + (ST)trans_s[c2 * ldT + c]);
                 } else {
                     for (int c2 = j; c2 < C; c2 += S)
-                        m2 = fmaxf(m2, zs[c2] + (valid ? __ldg(p.trans + (size_t)c2 * C + c) * SC : NEG));
+                        m2 = smax(m2, zs[c2] + (ST)(valid ? __ldg(p.trans + (size_t)c2 * C + c) * SC : NEG));
                 }
                 m2 = slice_max<S>(m2);
-                const float coef2 = valid ? w * ex2(gam + m2 - gm_n) : 0.0f;
+                const float coef2 = valid ? w * ex2((float)((gam + m2) - (ST)gm_n)) : 0.0f;
                 float s2 = 0.0f;
                 if constexpr (TM == 0) {
 #pragma unroll
                     for (int i = 0; i < CRR; ++i) {
-                        const float pq = ex2(zs[j * CRR + i] + tr[i] - m2);
+                        const float pq = ex2((float)(zs[j * CRR + i] + (ST)tr[i] - m2));
                         s2 += pq;
                         Et[i] = fmaf(pq, coef2, Et[i]);
                     }
                 } else if constexpr (TM == 1) {
                     for (int c2 = j; c2 < C; c2 += S) {
-                        const float pq = ex2(zs[c2] + trans_s[c2 * ldT + c] - m2);
+                        const float pq = ex2((float)(zs[c2] + (ST)trans_s[c2 * ldT + c] - m2));
                         s2 += pq;
                         if (valid) etr_s[c2 * ldT + c] += pq * coef2;
                     }
                 } else {
                     for (int c2 = j; c2 < C; c2 += S) {
-                        const float pq = ex2(zs[c2] + (valid ? __ldg(p.trans + (size_t)c2 * C + c) * SC : NEG) - m2);
+                        const float pq =
+                            ex2((float)(zs[c2] + (ST)(valid ? __ldg(p.trans + (size_t)c2 * C + c) * SC : NEG) - m2));
                         s2 += pq;
                         if (valid) etr_s[c2 * ldT + c] += pq * coef2;
                     }
                 }
                 s2 = slice_sum<S>(s2);
-                eta = valid ? (m2 - gm_n) + lg2(s2) : NEG;
+                eta = valid ? (m2 - (ST)gm_n) + (ST)lg2(s2) : (ST)NEG;
                 Fprev = coef2 * s2;
             }
             gm_next = gm_n;
@@ -819,19 +864,21 @@ struct RegChoice {
     size_t smem;
 };
 
-static size_t smem_bytes(const RegVariant& rv, int C, int W, int vpb, int tm, int mode) {
+static size_t smem_bytes(const RegVariant& rv, int C, int W, int vpb, int tm, int mode, bool xp) {
     const int cpw = 32 / rv.S, cpad = W * cpw, ldT = ld_trans(W, rv.S), G = W * 32;
+    const int stw = xp ? 2 : 1;  // state words (double / float)
     size_t fl = 0;
     if (tm == 1) fl += (size_t)C * ldT;
     if (!rv.lreg) fl += (size_t)rv.KR * G;
+    if (xp) fl += 1;  // alignment pad of the double rows
     if (mode == 2)
-        fl += (size_t)vpb * (2 * cpad + (tm != 0 ? C * ldT : 0));
+        fl += (size_t)vpb * (2 * cpad * stw + (tm != 0 ? C * ldT + 1 : 0));
     else
-        fl += (size_t)vpb * (2 * cpad + 2 * W);
+        fl += (size_t)vpb * (2 * cpad * stw + 2 * W);
     return fl * sizeof(float);
 }
 
-static RegChoice choose(int C, int L, int mode, bool sparse) {
+static RegChoice choose(int C, int L, int mode, bool sparse, bool xp = false) {
     RegChoice best{-1, 0, 0, 0, 0};
     double best_cost = 1e30;
     for (int v = 0; v < kNumVariants; ++v) {
@@ -846,8 +893,8 @@ static RegChoice choose(int C, int L, int mode, bool sparse) {
         int vpb = small1 ? 4 : maxt / (W * 32);
         if (vpb > 8) vpb = 8;
         if (!rv.lreg) vpb = 1;
-        while (vpb > 1 && smem_bytes(rv, C, W, vpb, tm, mode) > kSmemCap) --vpb;
-        const size_t sm = smem_bytes(rv, C, W, vpb, tm, mode);
+        while (vpb > 1 && smem_bytes(rv, C, W, vpb, tm, mode, xp) > kSmemCap) --vpb;
+        const size_t sm = smem_bytes(rv, C, W, vpb, tm, mode, xp);
         if (sm > kSmemCap) continue;
         // issue slots per frame ~ warps * (window + transitions per lane) (+ barrier cost when W > 1)
         const int crr = tm == 2 ? SPW : (tm == 0 ? (cpw + rv.S - 1) / rv.S : (C + rv.S - 1) / rv.S);
@@ -860,21 +907,22 @@ static RegChoice choose(int C, int L, int mode, bool sparse) {
     return best;
 }
 
-template <int MODE, int KR, int S, int TM, bool LREG, int MAXT>
+// MODE: 0 Viterbi, 1 log-semiring forward, 2 backward.  XP: extended-precision per-class state.
+template <int MODE, bool XP, int KR, int S, int TM, bool LREG, int MAXT>
 static int launch_one(const DpParams& p, const RegChoice& ch, cudaStream_t st) {
     const int blocks = (p.B + ch.VPB - 1) / ch.VPB;
     const int threads = ch.VPB * ch.W * 32;
     cudaError_t e = cudaSuccess;
     if constexpr (MODE == 0) {
-        auto k = dp_forward_kernel<true, KR, S, TM, LREG, MAXT>;
+        auto k = dp_forward_kernel<true, false, KR, S, TM, LREG, MAXT>;
         if (ch.smem > 48 * 1024) e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ch.smem);
         if (e == cudaSuccess) k<<<blocks, threads, ch.smem, st>>>(p);
     } else if constexpr (MODE == 1) {
-        auto k = dp_forward_kernel<false, KR, S, TM, LREG, MAXT>;
+        auto k = dp_forward_kernel<false, XP, KR, S, TM, LREG, MAXT>;
         if (ch.smem > 48 * 1024) e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ch.smem);
         if (e == cudaSuccess) k<<<blocks, threads, ch.smem, st>>>(p);
     } else {
-        auto k = dp_backward_kernel<KR, S, TM, LREG, MAXT>;
+        auto k = dp_backward_kernel<XP, KR, S, TM, LREG, MAXT>;
         if (ch.smem > 48 * 1024) e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ch.smem);
         if (e == cudaSuccess) k<<<blocks, threads, ch.smem, st>>>(p);
     }
@@ -885,64 +933,51 @@ static int launch_one(const DpParams& p, const RegChoice& ch, cudaStream_t st) {
     return check_launch("dp_reg kernel");
 }
 
-template <int MODE, int KR, int S>
+template <int MODE, bool XP, int KR, int S>
 static int launch_small(const DpParams& p, const RegChoice& ch, cudaStream_t st) {
     if (ch.tm == 2) {
-        return ch.W == 1 ? launch_one<MODE, KR, S, 2, true, kMaxThreadsSmall1>(p, ch, st)
-                         : launch_one<MODE, KR, S, 2, true, kMaxThreadsSmall>(p, ch, st);
+        return ch.W == 1 ? launch_one<MODE, XP, KR, S, 2, true, kMaxThreadsSmall1>(p, ch, st)
+                         : launch_one<MODE, XP, KR, S, 2, true, kMaxThreadsSmall>(p, ch, st);
     }
-    return ch.tm == 0 ? launch_one<MODE, KR, S, 0, true, kMaxThreadsSmall1>(p, ch, st)
-                      : launch_one<MODE, KR, S, 1, true, kMaxThreadsSmall>(p, ch, st);
+    return ch.tm == 0 ? launch_one<MODE, XP, KR, S, 0, true, kMaxThreadsSmall1>(p, ch, st)
+                      : launch_one<MODE, XP, KR, S, 1, true, kMaxThreadsSmall>(p, ch, st);
 }
-template <int MODE, int KR, int S>
+template <int MODE, bool XP, int KR, int S>
 static int launch_big(const DpParams& p, const RegChoice& ch, cudaStream_t st) {
-    return ch.tm == 2 ? launch_one<MODE, KR, S, 2, false, max_threads_big(KR, MODE)>(p, ch, st)
-                      : launch_one<MODE, KR, S, 1, false, max_threads_big(KR, MODE)>(p, ch, st);
+    return ch.tm == 2 ? launch_one<MODE, XP, KR, S, 2, false, max_threads_big(KR, MODE)>(p, ch, st)
+                      : launch_one<MODE, XP, KR, S, 1, false, max_threads_big(KR, MODE)>(p, ch, st);
 }
 
-template <int MODE>
+template <int MODE, bool XP>
 static int launch_mode(const DpParams& p, const RegChoice& ch, cudaStream_t st) {
     switch (ch.v) {
-        case 0: return launch_small<MODE, 10, 2>(p, ch, st);
-        case 1: return launch_small<MODE, 20, 1>(p, ch, st);
-        case 2: return launch_small<MODE, 13, 4>(p, ch, st);
-        case 3: return launch_small<MODE, 25, 2>(p, ch, st);
-        case 4: return launch_small<MODE, 25, 4>(p, ch, st);
-        case 5: return launch_small<MODE, 25, 8>(p, ch, st);
-        case 6: return launch_small<MODE, 32, 1>(p, ch, st);
-        case 7: return launch_big<MODE, 50, 4>(p, ch, st);
-        case 8: return launch_big<MODE, 50, 8>(p, ch, st);
-        case 9: return launch_big<MODE, 63, 8>(p, ch, st);
+        case 0: return launch_small<MODE, XP, 10, 2>(p, ch, st);
+        case 1: return launch_small<MODE, XP, 20, 1>(p, ch, st);
+        case 2: return launch_small<MODE, XP, 13, 4>(p, ch, st);
+        case 3: return launch_small<MODE, XP, 25, 2>(p, ch, st);
+        case 4: return launch_small<MODE, XP, 25, 4>(p, ch, st);
+        case 5: return launch_small<MODE, XP, 25, 8>(p, ch, st);
+        case 6: return launch_small<MODE, XP, 32, 1>(p, ch, st);
+        case 7: return launch_big<MODE, XP, 50, 4>(p, ch, st);
+        case 8: return launch_big<MODE, XP, 50, 8>(p, ch, st);
+        case 9: return launch_big<MODE, XP, 63, 8>(p, ch, st);
     }
     set_error("no register-resident DP variant for this shape");
     return -2;
 }
 
-// exported to hsmm_api.cu
-bool dp_reg_supported(int C, int L, int mode, bool sparse) { return choose(C, L, mode, sparse).v >= 0; }
-
-const char* dp_reg_name(int C, int L, int mode, bool sparse) {
-    static thread_local char buf[112];
-    RegChoice ch = choose(C, L, mode, sparse);
-    if (ch.v < 0) return "none";
-    static const char* tmn[] = {"trans-reg", "trans-smem", "trans-sparse"};
-    snprintf(buf, sizeof(buf), "reg<KR=%d,S=%d>/%s/%s/W=%d/VPB=%d/smem=%zu", kVariants[ch.v].KR, kVariants[ch.v].S,
-             tmn[ch.tm], kVariants[ch.v].lreg ? "len-reg" : "len-smem", ch.W, ch.VPB, ch.smem);
-    return buf;
-}
-
-int dp_reg_launch(DpParams p, int mode, cudaStream_t st) {
-    const bool sparse = (mode == 2) ? (p.trans_succ != nullptr) : (p.trans_pred != nullptr);
-    RegChoice ch = choose(p.C, p.L, mode, sparse);
-    if (ch.v < 0) {
-        set_error("shape C=%d L=%d not supported by the register-resident DP", p.C, p.L);
-        return -2;
+// one translation unit per (mode, precision) so that the variants compile in parallel
+#define HSMM_DP_DEFINE_LAUNCHER(NAME, MODE, XP)                                   \
+    int NAME(DpParams p, cudaStream_t st) {                                       \
+        const bool sparse = (MODE == 2) ? (p.trans_succ != nullptr) : (p.trans_pred != nullptr); \
+        RegChoice ch = choose(p.C, p.L, MODE, sparse, XP);                        \
+        if (ch.v < 0) {                                                           \
+            set_error("shape C=%d L=%d not supported by the register-resident DP", p.C, p.L); \
+            return -2;                                                            \
+        }                                                                         \
+        p.W = ch.W;                                                               \
+        p.VPB = ch.VPB;                                                           \
+        return launch_mode<MODE, XP>(p, ch, st);                                  \
     }
-    p.W = ch.W;
-    p.VPB = ch.VPB;
-    if (mode == 0) return launch_mode<0>(p, ch, st);
-    if (mode == 1) return launch_mode<1>(p, ch, st);
-    return launch_mode<2>(p, ch, st);
-}
 
 }  // namespace hsmm

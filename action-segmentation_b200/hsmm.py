@@ -37,6 +37,7 @@ def ldc_of(C):
 
 
 SPARSE_WIDTH = 4  # HSMM_SPARSE_WIDTH
+FLAG_F64_STATE = 1  # HSMM_FLAG_F64_STATE
 
 
 def sparse_transition_lists(allowed, device):
@@ -113,21 +114,24 @@ def viterbi_decode(em, C, init, trans, lenp, end, offset, lengths_i32, order=Non
     return spans, labels, score
 
 
-def logz_forward(em, C, init, trans, lenp, end, offset, lengths_i32, order=None, trans_pred=None):
-    """hsmm_logz_forward: returns (logz (B) float64, saved workspace)."""
+def logz_forward(em, C, init, trans, lenp, end, offset, lengths_i32, order=None, trans_pred=None, f64_state=False):
+    """hsmm_logz_forward: returns (logz (B) float64, saved workspace).  `f64_state` (HSMM_FLAG_F64_STATE): keep the
+    per-class DP state in double -- for score tensors that carry the -1e4 narration penalty."""
     _need_cuda(em, init, trans, lenp, end, offset, lengths_i32, order)
     lib = _lib.load()
     B, T, ldc = em.shape
     K = lenp.shape[0]
-    saved = torch.empty(lib.hsmm_logz_saved_bytes(B, T, C, K), device=em.device, dtype=torch.uint8)
+    flags = FLAG_F64_STATE if f64_state else 0
+    saved = torch.empty(lib.hsmm_logz_saved_bytes(B, T, C, K, flags), device=em.device, dtype=torch.uint8)
     logz = torch.empty(B, device=em.device, dtype=torch.float64)
     _lib.check(lib.hsmm_logz_forward(_p(em), ldc, _p(init), _p(trans), _p(trans_pred), _p(lenp), _p(end), _p(offset),
-                                     _p(lengths_i32), _p(order), B, T, C, K, _p(logz), _p(saved), _stream()),
+                                     _p(lengths_i32), _p(order), B, T, C, K, flags, _p(logz), _p(saved), _stream()),
                "hsmm_logz_forward")
     return logz, saved
 
 
-def logz_backward(em, C, init, trans, lenp, end, lengths_i32, order, grad_logz, saved, out=None, trans_succ=None):
+def logz_backward(em, C, init, trans, lenp, end, lengths_i32, order, grad_logz, saved, out=None, trans_succ=None,
+                  f64_state=False):
     """hsmm_logz_backward: returns (d_init (C), d_trans (C,C), d_len (K,C), d_em (B,T,ldc)).
     `out` may carry pre-allocated (zeroed) d_init/d_trans/d_len views of a packed gradient buffer."""
     lib = _lib.load()
@@ -143,8 +147,8 @@ def logz_backward(em, C, init, trans, lenp, end, lengths_i32, order, grad_logz, 
     d_em = torch.empty(B, T, ldc, device=dev, dtype=torch.float32)
     g = _f32(grad_logz)
     _lib.check(lib.hsmm_logz_backward(_p(em), ldc, _p(init), _p(trans), _p(trans_succ), _p(lenp), _p(end), _p(lengths_i32),
-                                      _p(order), _p(g), B, T, C, K, _p(saved), _p(d_init), _p(d_trans), _p(d_len), _p(d_em),
-                                      _stream()), "hsmm_logz_backward")
+                                      _p(order), _p(g), B, T, C, K, FLAG_F64_STATE if f64_state else 0, _p(saved), _p(d_init),
+                                      _p(d_trans), _p(d_len), _p(d_em), _stream()), "hsmm_logz_backward")
     return d_init, d_trans, d_len, d_em
 
 
@@ -196,9 +200,12 @@ class HsmmLogZ(torch.autograd.Function):
         em, rowterm, offset = emission_scores(features, means, cov_diag, penalty, lengths_i32)
         init_f, trans_f, lenp_f, end_f = _f32(init), _f32(trans), _f32(lenp), _f32(end)
         pred, succ = (None, None) if sparse is None else sparse
-        logz, saved = logz_forward(em, C, init_f, trans_f, lenp_f, end_f, offset, lengths_i32, order, trans_pred=pred)
+        # narration constraints put -1e4 offsets into the scores: keep the per-class DP state in double
+        xp = penalty is not None
+        logz, saved = logz_forward(em, C, init_f, trans_f, lenp_f, end_f, offset, lengths_i32, order, trans_pred=pred,
+                                   f64_state=xp)
         ctx.save_for_backward(features, means, cov_diag, em, init_f, trans_f, lenp_f, lengths_i32, saved)
-        ctx.end, ctx.order, ctx.C, ctx.succ = end_f, order, C, succ
+        ctx.end, ctx.order, ctx.C, ctx.succ, ctx.xp = end_f, order, C, succ, xp
         ctx.mark_non_differentiable(rowterm)
         return logz.to(torch.float32), logz, rowterm
 
@@ -210,7 +217,7 @@ class HsmmLogZ(torch.autograd.Function):
         if g64 is not None:
             g = g + g64.to(g.dtype)
         d_init, d_trans, d_len, d_em = logz_backward(em, C, init, trans, lenp, ctx.end, lengths_i32, ctx.order, g, saved,
-                                                     trans_succ=ctx.succ)
+                                                     trans_succ=ctx.succ, f64_state=ctx.xp)
         d_means = None
         if ctx.needs_input_grad[1]:
             wx, wsum = weighted_feature_sums(features, d_em, C, lengths_i32)

@@ -386,10 +386,12 @@ class SemiMarkovModule(nn.Module):
 
     def viterbi(self, features, lengths, valid_classes_per_instance, add_eos=True, use_mean_z=False,
                 additional_allowed_ends_per_instance=None, constraints=None, predict_single=False, return_elp=False,
-                return_labels=False):
+                return_labels=False, non_blocking=False):
         """semimarkov_modules.py:660-696: span-encoded predictions (b x T+1, CPU int64, global class
         ids, EOS = n_classes at position lengths[b]).  `return_labels=True` additionally returns the
-        per-frame labels the kernel emits (replacing semimarkov_utils.spans_to_labels)."""
+        per-frame labels the kernel emits (replacing semimarkov_utils.spans_to_labels).
+        `non_blocking=True` copies the results into pinned host memory asynchronously on the current
+        stream: the caller synchronises the stream (or device) before reading them."""
         assert add_eos, "only add_eos=True is implemented"
         valid_classes, C = self._valid_classes(valid_classes_per_instance)
         with torch.no_grad():
@@ -405,9 +407,16 @@ class SemiMarkovModule(nn.Module):
                                                    scores.offset, scores.lengths_i32, scores.order, ids.contiguous(),
                                                    want_labels=return_labels, want_score=False,
                                                    trans_pred=None if scores.sparse is None else scores.sparse[0])
-        out = [spans.cpu()]
+        def to_host(t):
+            if not non_blocking:
+                return t.cpu()
+            h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            h.copy_(t, non_blocking=True)
+            return h
+
+        out = [to_host(spans)]
         if return_elp:
             out.append(scores.elp)
         if return_labels:
-            out.append(labels.cpu())
+            out.append(to_host(labels))
         return out[0] if len(out) == 1 else tuple(out)

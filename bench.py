@@ -193,7 +193,7 @@ def device_step(tasks, streams, packed, layout, world):
 
 def e2e_step(models, tasks, host, streams):
     """Public API with host buffers: H2D of the step's features, loss + predictions read back."""
-    total = 0.0
+    lls = []
     preds = []
     for i, (m, tk) in enumerate(zip(models, tasks)):
         st = streams[i % len(streams)]
@@ -205,11 +205,13 @@ def e2e_step(models, tasks, host, streams):
                                      constraints=pen)
             (-ll).backward()
             spans, labels = m.viterbi(feats, tk.lengths, None, additional_allowed_ends_per_instance=[[] for _ in range(tk.V)],
-                                      constraints=pen, return_labels=True)
-            total += float(ll.detach())
-            preds.append(labels)
-    torch.cuda.synchronize()
-    return total, preds
+                                      constraints=pen, return_labels=True, non_blocking=True)
+            h = torch.empty((), dtype=torch.float32, pin_memory=True)
+            h.copy_(ll.detach(), non_blocking=True)
+            lls.append(h)
+            preds.append((spans, labels))
+    torch.cuda.synchronize()  # every task's loss, spans and labels are now in host memory
+    return float(sum(float(h) for h in lls)), preds
 
 
 def build_models(tasks, args):

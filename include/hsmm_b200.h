@@ -49,6 +49,12 @@ extern "C" {
 #define HSMM_ERR_SHAPE (-2)
 #define HSMM_ERR_CUDA (-3)
 #define HSMM_SPARSE_WIDTH 4
+/* flags of hsmm_logz_forward / hsmm_logz_backward / hsmm_logz_saved_bytes:
+ * HSMM_FLAG_F64_STATE keeps the O(C) per-frame DP state (and the saved forward quantities) in double.
+ * Set it when `em` carries large finite offsets -- the -1e4 narration penalty of
+ * models/semimarkov/semimarkov.py:25,227-232 -- so that classes whose scores differ by multiples of
+ * 1e4 keep their O(1) information; the O(C*K) span window stays in float either way. */
+#define HSMM_FLAG_F64_STATE 1
 
 /* Library version (major*100 + minor) and the last error message of the calling thread. */
 int hsmm_version(void);
@@ -79,10 +85,10 @@ int hsmm_emission(const float* X, const float* w, const float* bias, const float
 /*
  * Workspace sizes (bytes) for the DP entry points below, so that the caller allocates.
  *   hsmm_viterbi_workspace_bytes : back-pointer table
- *   hsmm_logz_saved_bytes        : forward quantities kept for hsmm_logz_backward
+ *   hsmm_logz_saved_bytes        : forward quantities kept for hsmm_logz_backward (depends on flags)
  */
 size_t hsmm_viterbi_workspace_bytes(int B, int Tmax, int C, int K);
-size_t hsmm_logz_saved_bytes(int B, int Tmax, int C, int K);
+size_t hsmm_logz_saved_bytes(int B, int Tmax, int C, int K, int flags);
 
 /*
  * Max-plus Viterbi decode.  Replaces `SemiMarkovCRF(scores, lengths).argmax` +
@@ -113,7 +119,7 @@ int hsmm_viterbi(const float* em, int ldc, const float* init, const float* trans
  */
 int hsmm_logz_forward(const float* em, int ldc, const float* init, const float* trans, const int32_t* trans_pred,
                       const float* lenp, const float* end, const double* offset, const int32_t* lengths,
-                      const int32_t* order, int B, int Tmax, int C, int K, double* out_logz, void* saved,
+                      const int32_t* order, int B, int Tmax, int C, int K, int flags, double* out_logz, void* saved,
                       void* stream);
 
 /*
@@ -123,11 +129,11 @@ int hsmm_logz_forward(const float* em, int ldc, const float* init, const float* 
  *   d_trans (C,C)  += sum_b g_b * E[# transitions c1 -> c2]            ([to,from])
  *   d_len (K,C)    += sum_b g_b * E[# segments of class c and length k]
  * and WRITES d_em (B,Tmax,ldc) = g_b * P(frame t has class c) (0 for t >= lengths[b]).
- * Must follow hsmm_logz_forward with the same inputs and `saved` buffer.
+ * Must follow hsmm_logz_forward with the same inputs, flags and `saved` buffer.
  */
 int hsmm_logz_backward(const float* em, int ldc, const float* init, const float* trans, const int32_t* trans_succ,
                        const float* lenp, const float* end, const int32_t* lengths, const int32_t* order,
-                       const float* grad_logz, int B, int Tmax, int C, int K, const void* saved,
+                       const float* grad_logz, int B, int Tmax, int C, int K, int flags, const void* saved,
                        float* d_init, float* d_trans, float* d_len, float* d_em, void* stream);
 
 /*
@@ -168,7 +174,8 @@ int hsmm_onehot_weights(const int32_t* labels, const int32_t* lengths, int B, in
 
 /* Introspection used by tests/bench: name of the DP kernel variant picked for a shape
  * ("reg<KR,S>/treg", "reg<KR,S>/tsmem", "ring") and how many kernels the library has launched. */
-const char* hsmm_dp_variant(int C, int K, int mode /*0 viterbi, 1 forward, 2 backward*/, int sparse);
+const char* hsmm_dp_variant(int C, int K, int mode /*0 viterbi, 1 forward, 2 backward*/,
+                            int flags /* bit 0: sparse transition lists, bit 1: f64 state */);
 uint64_t hsmm_launch_count(void);
 
 #ifdef __cplusplus

@@ -146,30 +146,35 @@ def test_viterbi_random_vs_oracle(shape):
         assert torch.allclose(score_d, score, rtol=1e-6, atol=1e-4)
 
 
+@pytest.mark.parametrize("f64_state", [False, True], ids=["f32state", "f64state"])
 @pytest.mark.parametrize("shape", SHAPES[:7] + SHAPES[10:], ids=lambda s: "B%d_T%d_C%d_K%d" % s[:4])
-def test_logz_and_counts_random_vs_oracle(shape):
-    """logZ within 1e-5 relative, expected counts within 1e-4 relative of the fp64 oracle."""
+def test_logz_and_counts_random_vs_oracle(shape, f64_state):
+    """logZ within 1e-5 relative, expected counts within 1e-4 relative of the fp64 oracle.  With the f64-state
+    kernels (HSMM_FLAG_F64_STATE, what the module selects whenever narration constraints are given) the
+    ordering-constrained shapes also carry -1e4 narration penalties on (nearly) every path -- inputs on which
+    the reference's own fp32 algorithm is only good to ~1e-3 (measured with oracle/reference_port.py:
+    E_trans 3e-3, E_em 7e-3 on the C=23 case)."""
     import action_segmentation_b200 as pkg
     B, Tmax, C, K, chain, ends = shape
     rng = np.random.default_rng(200 + C * 7 + K)
-    prob = random_problem(rng, B, Tmax, C, K, Tmin=1, chain=chain, ends=ends, narration=chain)
+    prob = random_problem(rng, B, Tmax, C, K, Tmin=1, chain=chain, ends=ends, narration=chain and f64_state)
     prob["lenp"] = O.clamp_len_table(prob["lenp"], Tmax)
     d = to_dev(prob)
     sp = sparse_lists(prob) if chain else (None, None)
     logz, saved = pkg.hsmm.logz_forward(d["em"], C, d["init"], d["trans"], d["lenp"], d["end"], None, d["lengths_i32"],
-                                        d["order"], trans_pred=sp[0])
+                                        d["order"], trans_pred=sp[0], f64_state=f64_state)
     w = rng.uniform(0.5, 1.5, size=B)
     g = torch.from_numpy(w).float().cuda()
     d_init, d_trans, d_len, d_em = pkg.hsmm.logz_backward(d["em"], C, d["init"], d["trans"], d["lenp"], d["end"],
-                                                         d["lengths_i32"], d["order"], g, saved, trans_succ=sp[1])
+                                                         d["lengths_i32"], d["order"], g, saved, trans_succ=sp[1],
+                                                         f64_state=f64_state)
     f32 = lambda x: x.astype(np.float32).astype(np.float64)  # noqa: E731
-    ref_logz, acc = O.batch_logz_and_counts(f32(prob["em"]), prob["lengths"], f32(prob["init"]), f32(prob["trans"]),
-                                            f32(prob["lenp"]), prob["end"], w)
+    p32 = dict(prob, em=f32(prob["em"]), init=f32(prob["init"]), trans=f32(prob["trans"]), lenp=f32(prob["lenp"]))
+    ref_logz, acc = O.batch_logz_and_counts(p32["em"], prob["lengths"], p32["init"], p32["trans"], p32["lenp"], prob["end"], w)
     assert np.allclose(logz.cpu().numpy(), ref_logz, rtol=1e-5, atol=1e-4)
-    assert rel_err(d_init.cpu().numpy(), acc["E_init"]) < 1e-4
-    assert rel_err(d_trans.cpu().numpy(), acc["E_trans"]) < 1e-4
-    assert rel_err(d_len.cpu().numpy(), acc["E_len"]) < 1e-4
-    assert rel_err(d_em.cpu().numpy()[:, :, :C], acc["E_em"]) < 1e-4
+    mine = dict(E_init=d_init, E_trans=d_trans, E_len=d_len, E_em=d_em[:, :, :C])
+    for k, v in mine.items():
+        assert rel_err(v.cpu().numpy(), acc[k]) < 1e-4, (k, rel_err(v.cpu().numpy(), acc[k]))
 
 
 @pytest.mark.parametrize("C,K", [(9, 20), (23, 20), (23, 100)])
@@ -203,10 +208,15 @@ def test_sparse_hint_degenerate_falls_back_to_dense(C, K):
     assert float(lz_d[1]) < -1e8 and float(lz_d[4]) < -1e8 and float(lz_d[0]) > -1e8
     assert torch.allclose(lz_s, lz_d, rtol=1e-6)
     assert torch.allclose(sc_s, sc_d, rtol=1e-6)
-    for b in (0, 2, 3, 5):
+    good = [0, 2, 3, 5]
+    for b in good:
         assert (sp_s[b] == sp_d[b]).all()
+    # feasible videos: identical frame posteriors whatever the hint
+    assert torch.allclose(gr_s[3][good], gr_d[3][good], rtol=1e-4, atol=1e-5)
+    # the two degenerate videos carry -1e9 on every path (fp32 resolves ~1e2 there): their posteriors and
+    # hence the summed counts agree to fp32-at-1e9 noise only
     for a, b_ in zip(gr_s, gr_d):
-        assert torch.allclose(a, b_, rtol=1e-4, atol=1e-5)
+        assert torch.allclose(a, b_, rtol=2e-3, atol=2e-3)
     f32 = lambda x: x.astype(np.float32).astype(np.float64)  # noqa: E731
     ref_logz, _ = O.batch_logz_and_counts(f32(prob["em"]), prob["lengths"], f32(prob["init"]), f32(prob["trans"]),
                                           f32(prob["lenp"]), prob["end"])

@@ -22,3 +22,13 @@ for case in ["unconstrained", "short_clamp", "constrained", "constrained_narrati
     for gk, pk in KEYMAP.items():
         mine = getattr(m, pk).grad.cpu().numpy()
         print("  ", gk, "mine-vs-oracle %.3e  ref-vs-oracle %.3e  mine-vs-ref %.3e" % (rel_err(mine, r["grads"][pk]), rel_err(g[gk], r["grads"][pk]), rel_err(mine, g[gk])))
+        if gk in ("g_trans",) and case == "constrained_narration":
+            np.set_printoptions(precision=8, suppress=True, linewidth=220)
+            d = mine - r["grads"][pk]
+            i, j = np.unravel_index(np.abs(d).argmax(), d.shape)
+            print("   worst", i, j, mine[i, j], r["grads"][pk][i, j], g[gk][i, j])
+            print("   mine  ", mine[:5, :5].ravel())
+            print("   oracle", r["grads"][pk][:5, :5].ravel())
+            print("   ref   ", g[gk][:5, :5].ravel())
+    if case == "constrained_narration":
+        print("logz golden", g["logz"])
