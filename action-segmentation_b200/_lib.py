@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libhsmm_b200.so")
 
 EXPORTS = [
-    "hsmm_version", "hsmm_last_error", "hsmm_emission", "hsmm_viterbi_workspace_bytes", "hsmm_logz_saved_bytes",
+    "hsmm_version", "hsmm_last_error", "hsmm_emission", "hsmm_emission_workspace_bytes", "hsmm_viterbi_workspace_bytes", "hsmm_logz_saved_bytes",
     "hsmm_viterbi", "hsmm_logz_forward", "hsmm_logz_backward", "hsmm_weighted_feature_sums", "hsmm_gold_score",
     "hsmm_feature_moments", "hsmm_onehot_weights", "hsmm_dp_variant", "hsmm_launch_count",
 ]
@@ -40,7 +40,9 @@ def load():
     lib.hsmm_viterbi_workspace_bytes.argtypes = [i, i, i, i]
     lib.hsmm_logz_saved_bytes.restype = sz
     lib.hsmm_logz_saved_bytes.argtypes = [i, i, i, i, i]
-    lib.hsmm_emission.argtypes = [p, p, p, p, f, p, p, i, i, i, i, i, p, p, p, p]
+    lib.hsmm_emission.argtypes = [p, p, p, p, f, p, p, i, i, i, i, i, p, p, p, p, p]
+    lib.hsmm_emission_workspace_bytes.restype = sz
+    lib.hsmm_emission_workspace_bytes.argtypes = [i, i]
     lib.hsmm_viterbi.argtypes = [p, i, p, p, p, p, p, p, p, p, p, i, i, i, i, p, p, p, p, p]
     lib.hsmm_logz_forward.argtypes = [p, i, p, p, p, p, p, p, p, p, i, i, i, i, i, p, p, p]
     lib.hsmm_logz_backward.argtypes = [p, i, p, p, p, p, p, p, p, p, i, i, i, i, i, p, p, p, p, p, p]

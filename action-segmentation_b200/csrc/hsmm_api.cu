@@ -44,6 +44,9 @@ const char* dp_reg_name(int C, int L, int mode, bool sparse, bool xp);
 int dp_reg_launch(DpParams p, int mode, cudaStream_t st);
 int launch_emission(const float*, const float*, const float*, const float*, float, const float*, const int32_t*, int, int, int,
                     int, int, float*, float*, double*, cudaStream_t);
+size_t emission_tc_workspace_bytes(int D, int C);
+int launch_emission_tc(const float*, const float*, const float*, const float*, float, const float*, const int32_t*, int, int,
+                       int, int, int, float*, float*, double*, void*, int, cudaStream_t);
 int launch_weighted_sums(const float*, const float*, int, const int32_t*, int, int, int, int, float*, float*, int, cudaStream_t);
 int launch_moments(const float*, const int32_t*, int, int, int, double*, double*, int, cudaStream_t);
 int launch_onehot(const int32_t*, const int32_t*, int, int, int, int, float*, int, cudaStream_t);
@@ -127,7 +130,7 @@ size_t hsmm_logz_saved_bytes(int B, int Tmax, int C, int K, int flags) {
 
 int hsmm_emission(const float* X, const float* w, const float* bias, const float* inv_var, float row_const,
                   const float* penalty, const int32_t* lengths, int B, int Tmax, int D, int C, int ldc, float* em,
-                  float* rowterm, double* offset, void* stream) {
+                  float* rowterm, double* offset, void* workspace, void* stream) {
     if (!X || !w || !bias || !inv_var || !lengths || !em || !rowterm || !offset) {
         set_error("hsmm_emission: null pointer");
         return HSMM_ERR_ARG;
@@ -140,9 +143,15 @@ int hsmm_emission(const float* X, const float* w, const float* bias, const float
         set_error("hsmm_emission: B=%d exceeds grid.y; split the batch", B);
         return HSMM_ERR_SHAPE;
     }
+    // tensor-core path (TMA + tcgen05, 3xTF32) when the shape is eligible and a workspace was given
+    const int rc = launch_emission_tc(X, w, bias, inv_var, row_const, penalty, lengths, B, Tmax, D, C, ldc, em, rowterm, offset,
+                                      workspace, num_sms(), (cudaStream_t)stream);
+    if (rc <= 0) return rc;
     return launch_emission(X, w, bias, inv_var, row_const, penalty, lengths, B, Tmax, D, C, ldc, em, rowterm, offset,
                            (cudaStream_t)stream);
 }
+
+size_t hsmm_emission_workspace_bytes(int D, int C) { return emission_tc_workspace_bytes(D, C); }
 
 int hsmm_viterbi(const float* em, int ldc, const float* init, const float* trans, const int32_t* trans_pred, const float* lenp,
                  const float* end, const double* offset, const int32_t* lengths, const int32_t* order, const int32_t* class_ids, int B,

@@ -1,0 +1,523 @@
+// Emission scoring on the 5th-generation tensor cores (sm_100a): TMA -> shared memory -> tcgen05.mma
+// (kind::tf32, accumulators in TMEM) -> tcgen05.ld epilogue.
+//
+//   em'[t,c] = x_t . w_c + bias_c (+ penalty) - shift_t        (semimarkov_modules.py:324-381)
+//
+// is a (frames x D) . (D x C) contraction with arithmetic intensity C/2 flop/B: HBM-bound, so the job of
+// the kernel is to stream X exactly once at full bandwidth while the tensor pipe does the flops.
+// Plain TF32 (10-bit mantissa) is NOT accurate enough for the 1e-4 tolerance on the marginals at
+// D = 200, so operands are split in registers into a tf32-exact "big" part and a "small" remainder
+// (x = xb + xs, w = wb + ws) and three MMAs accumulate xb.wb + xs.wb + xb.ws in fp32 (3xTF32: the
+// dropped xs.ws term is ~2^-22 relative).
+//
+// Persistent CTAs (one per SM), tile = 128 consecutive rows of the flattened (B*Tmax, D) feature matrix:
+//   warp 0      TMA producer: X chunks of 32 floats (one 128-byte swizzle row per frame) into a ring
+//   warp 1      MMA issuer (one lane) + TMEM allocation; 2 accumulators of NPAD columns (double buffer)
+//   warps 2..5  "converters": split the landed chunk into big/small in place (+ the row term
+//               -0.5 sum x^2/var), then the epilogue of the PREVIOUS tile (TMEM -> registers: bias,
+//               penalty, per-frame shift, row term, f64 per-video offset) while the tensor core works on
+//               the current one.  Thread <-> frame, which is also the TMEM lane mapping of tcgen05.ld.
+// Tiles that lie entirely in the zero padding behind a video are never loaded.
+#include <cuda.h>
+
+#include "hsmm_common.cuh"
+
+namespace hsmm {
+
+namespace etc {
+
+constexpr int TILE_M = 128;       // frames per tile = UMMA M
+constexpr int KC = 32;            // floats per chunk = one 128-byte swizzle row
+constexpr int CHUNK_BYTES = TILE_M * KC * 4;  // 16 KB
+constexpr int STAGE_BYTES = 2 * CHUNK_BYTES;  // big + small
+constexpr int THREADS = 192;
+constexpr int ACC_STRIDE = 64;    // TMEM columns between the two accumulators
+constexpr int TMEM_COLS = 128;
+constexpr int MAX_STAGES = 6;
+constexpr uint32_t TF32_MASK = 0xffffe000u;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
+// 16 consecutive accumulator columns of this thread's TMEM lane
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128-byte swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
+// start address >> 4 in [0,14), LBO (unused for swizzled K-major) = 1 in [16,30), SBO = 1024 B (8 rows of
+// 128 B) >> 4 in [32,46), version = 1 in [46,48), layout SWIZZLE_128B = 2 in [61,64).
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3ffffu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+           ((uint64_t)2 << 61);
+}
+
+struct Params {
+    const float* bias;
+    const float* inv_var;
+    const float* penalty;
+    const int32_t* lengths;
+    float* em;
+    float* rowterm;
+    double* offset;
+    float row_const;
+    int B, Tmax, D, C, ldc;
+    int npad;     // classes padded to a multiple of 16 (UMMA N)
+    int nchunk;   // ceil(D / 32)
+    int nstage;   // ring depth
+    int ntiles;   // ceil(B*Tmax / 128)
+};
+
+// does the tile [r0, r0+128) of the flattened rows contain a frame of a video (t < length)?
+__device__ __forceinline__ bool tile_active(const Params& p, int tile) {
+    const long long r0 = (long long)tile * TILE_M;
+    const long long r1 = min(r0 + TILE_M, (long long)p.B * p.Tmax);
+    int b = (int)(r0 / p.Tmax);
+    long long start = r0;
+    while (start < r1) {
+        const int t = (int)(start - (long long)b * p.Tmax);
+        if (t < p.lengths[b]) return true;
+        ++b;
+        start = (long long)b * p.Tmax;
+    }
+    return false;
+}
+
+template <int NB>  // NPAD = 16 * NB
+__global__ void __launch_bounds__(THREADS, 1)
+emission_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w, const Params p) {
+    constexpr int NPAD = 16 * NB;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // carve: [W: nchunk x (big NPAD x 128 B, small NPAD x 128 B)] [stages] [bias NPAD] [inv_var nchunk*32] [barriers]
+    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* w_s = base;
+    const int w_chunk_bytes = 2 * NPAD * 128;
+    uint8_t* st_s = w_s + (size_t)p.nchunk * w_chunk_bytes;
+    float* bias_s = reinterpret_cast<float*>(st_s + (size_t)p.nstage * STAGE_BYTES);
+    float* iv_s = bias_s + NPAD;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(iv_s + p.nchunk * KC);
+    uint64_t* full = bars;                     // TMA -> converters
+    uint64_t* conv = full + MAX_STAGES;        // converters -> MMA
+    uint64_t* empty = conv + MAX_STAGES;       // MMA -> TMA
+    uint64_t* tfull = empty + MAX_STAGES;      // MMA -> epilogue   [2]
+    uint64_t* tempty = tfull + 2;              // epilogue -> MMA   [2]
+    uint64_t* wbar = tempty + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int klast = (p.D - (p.nchunk - 1) * KC + 7) / 8;  // k-steps (of 8) in the last chunk
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.nstage; ++s) {
+            mbar_init(full + s, 1);
+            mbar_init(conv + s, 128);
+            mbar_init(empty + s, 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tfull + a, 1);
+            mbar_init(tempty + a, 128);
+        }
+        mbar_init(wbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (warp >= 2) {
+        for (int i = threadIdx.x - 64; i < NPAD; i += 128) bias_s[i] = (i < p.C) ? p.bias[i] : 0.0f;
+        for (int i = threadIdx.x - 64; i < p.nchunk * KC; i += 128) iv_s[i] = (i < p.D) ? p.inv_var[i] : 0.0f;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            mbar_arrive_expect_tx(wbar, (uint32_t)(p.nchunk * w_chunk_bytes));
+            for (int ch = 0; ch < p.nchunk; ++ch) {
+                tma_load_2d(w_s + (size_t)ch * w_chunk_bytes, &tmap_w, wbar, ch * KC, 0);
+                tma_load_2d(w_s + (size_t)ch * w_chunk_bytes + NPAD * 128, &tmap_w, wbar, ch * KC, NPAD);
+            }
+            int st = 0;
+            uint32_t ph = 0;
+            for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+                if (!tile_active(p, tile)) continue;
+                for (int ch = 0; ch < p.nchunk; ++ch) {
+                    mbar_wait(empty + st, ph ^ 1);
+                    mbar_arrive_expect_tx(full + st, CHUNK_BYTES);
+                    tma_load_2d(st_s + (size_t)st * STAGE_BYTES, &tmap_x, full + st, ch * KC, tile * TILE_M);
+                    if (++st == p.nstage) {
+                        st = 0;
+                        ph ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NPAD >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+            mbar_wait(wbar, 0);
+            int st = 0;
+            uint32_t ph = 0;
+            int acc = 0;
+            uint32_t accph = 0;
+            for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+                if (!tile_active(p, tile)) continue;
+                mbar_wait(tempty + acc, accph ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * ACC_STRIDE;
+                uint32_t accum = 0;
+                for (int ch = 0; ch < p.nchunk; ++ch) {
+                    mbar_wait(conv + st, ph);
+                    tc_fence_after();
+                    const uint32_t xb = smem_u32(st_s + (size_t)st * STAGE_BYTES);
+                    const uint32_t xs = xb + CHUNK_BYTES;
+                    const uint32_t wb = smem_u32(w_s + (size_t)ch * w_chunk_bytes);
+                    const uint32_t ws = wb + NPAD * 128;
+                    const int ksteps = (ch == p.nchunk - 1) ? klast : 4;
+                    for (int ks = 0; ks < ksteps; ++ks) {
+                        const uint32_t ko = ks * 32;  // 8 tf32 = 32 bytes inside the 128-byte swizzle row
+                        tc_mma_tf32(d_tmem, smem_desc_sw128(xs + ko), smem_desc_sw128(wb + ko), idesc, accum);
+                        accum = 1;
+                        tc_mma_tf32(d_tmem, smem_desc_sw128(xb + ko), smem_desc_sw128(ws + ko), idesc, 1);
+                        tc_mma_tf32(d_tmem, smem_desc_sw128(xb + ko), smem_desc_sw128(wb + ko), idesc, 1);
+                    }
+                    tc_commit(empty + st);  // the stage may be refilled once these MMAs have read it
+                    if (++st == p.nstage) {
+                        st = 0;
+                        ph ^= 1;
+                    }
+                }
+                tc_commit(tfull + acc);
+                if (++acc == 2) {
+                    acc = 0;
+                    accph ^= 1;
+                }
+            }
+        }
+    } else {
+        // ===================== converters + epilogue (128 threads, thread <-> frame) =====================
+        const int q = warp & 3;              // TMEM lane quarter this warp may read
+        const int r = q * 32 + lane;         // row inside the tile
+        const long long total_rows = (long long)p.B * p.Tmax;
+        int st = 0;
+        uint32_t ph = 0;
+        int acc = 0;
+        uint32_t accph = 0;
+        // pending epilogue (previous tile)
+        int pend_tile = -1;
+        bool pend_active = false;
+        float pend_rowsq = 0.0f;
+        int pend_acc = 0;
+        uint32_t pend_accph = 0;
+
+        auto epilogue = [&](int tile, bool active, float rowsq, int a, uint32_t aph) {
+            const long long row = (long long)tile * TILE_M + r;
+            const bool in_range = row < total_rows;
+            int b = 0, t = 0;
+            bool live = false;
+            if (in_range) {
+                b = (int)(row / p.Tmax);
+                t = (int)(row - (long long)b * p.Tmax);
+                live = t < p.lengths[b];
+            }
+            float v[NPAD];
+            if (active) {
+                mbar_wait(tfull + a, aph);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + a * ACC_STRIDE;
+#pragma unroll
+                for (int i = 0; i < NB; ++i) tc_ld16(taddr + 16 * i, v + 16 * i);
+                tc_wait_ld();
+                tc_fence_before();
+                mbar_arrive(tempty + a);
+            }
+            double contrib = 0.0;
+            if (in_range) {
+                float* em_r = p.em + (size_t)row * p.ldc;
+                float rt = 0.0f;
+                if (live) {
+                    // live implies active: the accumulators are valid
+                    const float* pen_r = p.penalty ? p.penalty + (size_t)row * p.C : nullptr;
+                    float m = NEG;
+#pragma unroll
+                    for (int c = 0; c < NPAD; ++c) {
+                        v[c] += bias_s[c];
+                        if (c < p.C) m = fmaxf(m, v[c] + (pen_r ? __ldg(pen_r + c) : 0.0f));
+                    }
+                    // shift by the best penalised score; the penalty (-1e4 per offending frame) is added AFTER
+                    // the shift so that the large number meets an O(1) one exactly once, like the reference's
+                    // elp + constraints (semimarkov_modules.py:379-380)
+#pragma unroll
+                    for (int c = 0; c < NPAD; ++c) {
+                        float o = 0.0f;
+                        if (c < p.C) {
+                            o = v[c] - m;
+                            if (pen_r) o += __ldg(pen_r + c);
+                        }
+                        v[c] = o;
+                    }
+                    rt = (-0.5f * rowsq + p.row_const) + m;
+                    contrib = (double)rt;
+                } else {
+#pragma unroll
+                    for (int c = 0; c < NPAD; ++c) v[c] = 0.0f;
+                }
+#pragma unroll
+                for (int c4 = 0; c4 < NPAD / 4; ++c4)
+                    if (c4 * 4 < p.ldc)
+                        *reinterpret_cast<float4*>(em_r + c4 * 4) = make_float4(v[c4 * 4], v[c4 * 4 + 1], v[c4 * 4 + 2], v[c4 * 4 + 3]);
+                p.rowterm[row] = rt;
+            }
+            // per-video offset: one f64 atomic per warp when the warp sits inside one video
+            const int b0 = __shfl_sync(FULL, b, 0);
+            const bool same = __all_sync(FULL, !in_range || b == b0);
+            if (same) {
+                contrib = warp_sum(contrib);
+                if (lane == 0 && contrib != 0.0) atomicAdd(p.offset + b0, contrib);
+            } else if (live) {
+                atomicAdd(p.offset + b, contrib);
+            }
+        };
+
+        for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+            const bool active = tile_active(p, tile);
+            float rowsq = 0.0f;
+            if (active) {
+                for (int ch = 0; ch < p.nchunk; ++ch) {
+                    mbar_wait(full + st, ph);
+                    uint8_t* xb = st_s + (size_t)st * STAGE_BYTES + (size_t)r * 128;
+                    uint8_t* xs = xb + CHUNK_BYTES;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int pj = (i + r) & 7;            // physical 16-byte slot (rotated: conflict-free)
+                        const int lj = pj ^ (r & 7);           // logical slot under the 128-byte swizzle
+                        float4 x = *reinterpret_cast<float4*>(xb + pj * 16);
+                        const float4 iv = *reinterpret_cast<const float4*>(iv_s + ch * KC + lj * 4);
+                        rowsq = fmaf(x.x * x.x, iv.x, rowsq);
+                        rowsq = fmaf(x.y * x.y, iv.y, rowsq);
+                        rowsq = fmaf(x.z * x.z, iv.z, rowsq);
+                        rowsq = fmaf(x.w * x.w, iv.w, rowsq);
+                        float4 big, sml;
+                        big.x = __uint_as_float(__float_as_uint(x.x) & TF32_MASK);
+                        big.y = __uint_as_float(__float_as_uint(x.y) & TF32_MASK);
+                        big.z = __uint_as_float(__float_as_uint(x.z) & TF32_MASK);
+                        big.w = __uint_as_float(__float_as_uint(x.w) & TF32_MASK);
+                        sml.x = x.x - big.x;
+                        sml.y = x.y - big.y;
+                        sml.z = x.z - big.z;
+                        sml.w = x.w - big.w;
+                        *reinterpret_cast<float4*>(xb + pj * 16) = big;
+                        *reinterpret_cast<float4*>(xs + pj * 16) = sml;
+                    }
+                    fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
+                    mbar_arrive(conv + st);
+                    if (++st == p.nstage) {
+                        st = 0;
+                        ph ^= 1;
+                    }
+                }
+            }
+            if (pend_tile >= 0) epilogue(pend_tile, pend_active, pend_rowsq, pend_acc, pend_accph);
+            pend_tile = tile;
+            pend_active = active;
+            pend_rowsq = rowsq;
+            pend_acc = acc;
+            pend_accph = accph;
+            if (active && ++acc == 2) {
+                acc = 0;
+                accph ^= 1;
+            }
+        }
+        if (pend_tile >= 0) epilogue(pend_tile, pend_active, pend_rowsq, pend_acc, pend_accph);
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// w (C, D) -> wsplit (2*npad, dpad): rows [0, npad) tf32-exact big parts, rows [npad, 2 npad) remainders; zero padded
+__global__ void emission_split_w_kernel(const float* __restrict__ w, int C, int D, int npad, int dpad, float* __restrict__ out) {
+    const int n = npad * dpad;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int c = i / dpad, d = i - c * dpad;
+        float x = (c < C && d < D) ? w[(size_t)c * D + d] : 0.0f;
+        const float big = __uint_as_float(__float_as_uint(x) & TF32_MASK);
+        out[i] = big;
+        out[n + i] = x - big;
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+static bool make_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstr[1] = {cols * sizeof(float)};
+    cuuint32_t box[2] = {(cuuint32_t)KC, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+struct Plan {
+    int npad, nchunk, nstage;
+    size_t smem;
+};
+
+static bool plan(int D, int C, Plan* pl) {
+    if (C > 64 || D % 4 != 0 || D < 4) return false;
+    pl->npad = (C + 15) / 16 * 16;
+    pl->nchunk = (D + KC - 1) / KC;
+    const size_t fixed = 1024 + (size_t)pl->nchunk * 2 * pl->npad * 128 + (size_t)(pl->npad + pl->nchunk * KC) * 4 +
+                         (3 * MAX_STAGES + 5) * 8 + 16;
+    const size_t cap = 227 * 1024;
+    if (fixed + 2 * (size_t)STAGE_BYTES > cap) return false;
+    int ns = (int)((cap - fixed) / STAGE_BYTES);
+    if (ns > MAX_STAGES) ns = MAX_STAGES;
+    pl->nstage = ns;
+    pl->smem = fixed + (size_t)ns * STAGE_BYTES;
+    return true;
+}
+
+}  // namespace etc
+
+size_t emission_tc_workspace_bytes(int D, int C) {
+    etc::Plan pl;
+    if (!etc::plan(D, C, &pl)) return 0;
+    return (size_t)2 * pl.npad * pl.nchunk * etc::KC * sizeof(float);
+}
+
+// returns 1 when the shape / alignment is not eligible (caller falls back to the SIMT kernel), 0 on launch, < 0 on error
+int launch_emission_tc(const float* X, const float* w, const float* bias, const float* inv_var, float row_const,
+                       const float* penalty, const int32_t* lengths, int B, int Tmax, int D, int C, int ldc, float* em,
+                       float* rowterm, double* offset, void* workspace, int num_sms, cudaStream_t st) {
+    using namespace etc;
+    Plan pl;
+    if (!workspace || !plan(D, C, &pl)) return 1;
+    if ((reinterpret_cast<uintptr_t>(X) & 15) || (reinterpret_cast<uintptr_t>(workspace) & 15) ||
+        (reinterpret_cast<uintptr_t>(em) & 15) || ldc % 4 != 0 || ldc > pl.npad)
+        return 1;
+    const long long rows = (long long)B * Tmax;
+    if (rows >= (1ll << 31) - TILE_M) return 1;
+    const int dpad = pl.nchunk * KC;
+    CUtensorMap mx, mw;
+    if (!make_map(&mx, X, (uint64_t)rows, (uint64_t)D, TILE_M)) return 1;
+    if (!make_map(&mw, workspace, (uint64_t)(2 * pl.npad), (uint64_t)dpad, (uint32_t)pl.npad)) return 1;
+
+    cudaError_t e = cudaMemsetAsync(offset, 0, sizeof(double) * B, st);
+    if (e != cudaSuccess) {
+        set_error("memset offset: %s", cudaGetErrorString(e));
+        return -3;
+    }
+    emission_split_w_kernel<<<(pl.npad * dpad + 255) / 256, 256, 0, st>>>(w, C, D, pl.npad, dpad, reinterpret_cast<float*>(workspace));
+    int rc = check_launch("emission_split_w_kernel");
+    if (rc) return rc;
+
+    Params p;
+    p.bias = bias; p.inv_var = inv_var; p.penalty = penalty; p.lengths = lengths; p.em = em; p.rowterm = rowterm;
+    p.offset = offset; p.row_const = row_const; p.B = B; p.Tmax = Tmax; p.D = D; p.C = C; p.ldc = ldc;
+    p.npad = pl.npad; p.nchunk = pl.nchunk; p.nstage = pl.nstage;
+    p.ntiles = (int)((rows + TILE_M - 1) / TILE_M);
+    int grid = num_sms < p.ntiles ? num_sms : p.ntiles;
+    if (grid < 1) grid = 1;
+
+#define HSMM_ETC_LAUNCH(NB)                                                                                          \
+    {                                                                                                                \
+        e = cudaFuncSetAttribute(emission_tc_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem); \
+        if (e == cudaSuccess) emission_tc_kernel<NB><<<grid, THREADS, pl.smem, st>>>(mx, mw, p);                      \
+    }
+    switch (pl.npad / 16) {
+        case 1: HSMM_ETC_LAUNCH(1) break;
+        case 2: HSMM_ETC_LAUNCH(2) break;
+        case 3: HSMM_ETC_LAUNCH(3) break;
+        default: HSMM_ETC_LAUNCH(4) break;
+    }
+#undef HSMM_ETC_LAUNCH
+    if (e != cudaSuccess) {
+        set_error("emission_tc smem attr: %s", cudaGetErrorString(e));
+        return -3;
+    }
+    return check_launch("emission_tc_kernel");
+}
+
+}  // namespace hsmm

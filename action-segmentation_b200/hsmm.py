@@ -75,8 +75,9 @@ def emission_params(means, cov_diag):
     return w, bias, inv_var, row_const
 
 
-def emission_scores(features, means, cov_diag, penalty, lengths_i32):
-    """hsmm_emission: returns (em (B,T,ldc), rowterm (B,T), offset (B) float64)."""
+def emission_scores(features, means, cov_diag, penalty, lengths_i32, tensor_cores=True):
+    """hsmm_emission: returns (em (B,T,ldc), rowterm (B,T), offset (B) float64).  `tensor_cores=False` withholds
+    the workspace, which selects the SIMT kernel (used by the tests to compare the two)."""
     _need_cuda(features, means, cov_diag, penalty, lengths_i32)
     lib = _lib.load()
     B, T, D = features.shape
@@ -91,8 +92,10 @@ def emission_scores(features, means, cov_diag, penalty, lengths_i32):
     em = torch.empty(B, T, ldc, device=X.device, dtype=torch.float32)
     rowterm = torch.empty(B, T, device=X.device, dtype=torch.float32)
     offset = torch.empty(B, device=X.device, dtype=torch.float64)
+    ws_bytes = lib.hsmm_emission_workspace_bytes(D, C) if tensor_cores else 0
+    ws = torch.empty(ws_bytes, device=X.device, dtype=torch.uint8) if ws_bytes else None
     _lib.check(lib.hsmm_emission(_p(X), _p(w), _p(bias), _p(inv_var), row_const, _p(pen), _p(lengths_i32), B, T, D, C, ldc,
-                                 _p(em), _p(rowterm), _p(offset), _stream()), "hsmm_emission")
+                                 _p(em), _p(rowterm), _p(offset), _p(ws), _stream()), "hsmm_emission")
     return em, rowterm, offset
 
 

@@ -77,10 +77,15 @@ const char* hsmm_last_error(void);
  *
  * X (B,Tmax,D); w (C,D); bias (C); inv_var (D); penalty (B,Tmax,C) or NULL;
  * em (B,Tmax,ldc) out; rowterm (B,Tmax) out; offset (B) out (double, overwritten).
+ * workspace: hsmm_emission_workspace_bytes(D, C) bytes (16-byte aligned) or NULL.  With a workspace and an
+ * eligible shape (C <= 64, D % 4 == 0, X 16-byte aligned) the contraction runs on the tensor cores
+ * (TMA-fed tcgen05.mma, operands split 3xTF32 so that the result is fp32-accurate); otherwise on a
+ * SIMT fp32 kernel.  hsmm_emission_workspace_bytes returns 0 for shapes without a tensor-core plan.
  */
+size_t hsmm_emission_workspace_bytes(int D, int C);
 int hsmm_emission(const float* X, const float* w, const float* bias, const float* inv_var, float row_const,
                   const float* penalty, const int32_t* lengths, int B, int Tmax, int D, int C, int ldc,
-                  float* em, float* rowterm, double* offset, void* stream);
+                  float* em, float* rowterm, double* offset, void* workspace, void* stream);
 
 /*
  * Workspace sizes (bytes) for the DP entry points below, so that the caller allocates.

@@ -35,6 +35,51 @@ def test_emission_golden(golden, case):
         assert rel_err(elp[b, :T], g["elp"][b, :T]) < 1e-5
 
 
+@pytest.mark.parametrize("B,Tmax,D,C,pen", [(7, 300, 200, 23, False), (5, 257, 200, 13, True), (3, 700, 64, 48, False),
+                                            (4, 130, 200, 7, True), (2, 1000, 300, 64, False), (3, 90, 36, 5, False)])
+def test_emission_tensor_core_vs_oracle(B, Tmax, D, C, pen):
+    """hsmm_emission on the tcgen05/TMA path (3xTF32) against the fp64 oracle (semimarkov_modules.py:324-381)
+    and against the SIMT fp32 kernel: same em/rowterm/offset contract, fp32-level accuracy."""
+    import action_segmentation_b200 as pkg
+    assert pkg._lib.load().hsmm_emission_workspace_bytes(D, C) > 0
+    rng = np.random.default_rng(B * 1000 + D + C)
+    lengths = rng.integers(1, Tmax + 1, size=B)
+    lengths[0] = Tmax
+    means = rng.normal(size=(C, D)) * 0.5
+    cov = rng.uniform(0.5, 1.5, size=D)
+    lab = rng.integers(0, C, size=(B, Tmax))
+    X = (means[lab] + rng.normal(size=(B, Tmax, D))).astype(np.float32)
+    for b in range(B):
+        X[b, lengths[b]:] = 0
+    penalty = None
+    if pen:
+        penalty = np.where(rng.uniform(size=(B, Tmax, C)) < 0.2, -1e4, 0.0).astype(np.float32)
+        penalty[:, :, 0] = 0
+    dev = lambda a: None if a is None else torch.from_numpy(np.ascontiguousarray(a)).cuda()  # noqa: E731
+    f32 = lambda a: torch.from_numpy(a.astype(np.float32)).cuda()  # noqa: E731
+    li = torch.from_numpy(lengths).to(torch.int32).cuda()
+    outs = []
+    for tc in (True, False):
+        em, rowterm, offset = pkg.hsmm.emission_scores(dev(X), f32(means), f32(cov), dev(penalty), li, tensor_cores=tc)
+        outs.append((em.cpu().numpy().astype(np.float64), rowterm.cpu().numpy().astype(np.float64), offset.cpu().numpy()))
+    m32 = means.astype(np.float32).astype(np.float64)
+    c32 = cov.astype(np.float32).astype(np.float64)
+    ref = O.emission_log_probs(X.astype(np.float64), m32, c32, None if penalty is None else penalty.astype(np.float64))
+    for em, rowterm, offset in outs:
+        assert em.shape[2] == pkg.hsmm.ldc_of(C)
+        elp = em[:, :, :C] + rowterm[:, :, None]
+        for b, T in enumerate(lengths):
+            scale = np.abs(ref[b, :T]).max()
+            assert np.abs(elp[b, :T] - ref[b, :T]).max() < 2e-6 * scale + 1e-3 * (1 if pen else 0), (b, np.abs(elp[b, :T] - ref[b, :T]).max())
+            assert em[b, :T, :C].max(axis=1).max() <= 1e-6 and (em[b, :T, :C].max(axis=1) > -1e-3).all()  # best class 0
+            assert (em[b, T:] == 0).all() and (rowterm[b, T:] == 0).all()
+            assert abs(offset[b] - rowterm[b, :T].sum()) < 1e-6 * abs(offset[b]) + 1e-6
+    # the two kernels agree on the class-relative scores to fp32 rounding of the dot products
+    d = np.abs(outs[0][0] - outs[1][0])
+    unpen = np.ones_like(d, dtype=bool) if penalty is None else np.pad(penalty == 0, ((0, 0), (0, 0), (0, d.shape[2] - C)))
+    assert d[unpen].max() < 4e-6 * np.abs(ref).max(), d[unpen].max()
+
+
 @pytest.mark.parametrize("case", CASES)
 def test_loglik_and_grads_golden(golden, case):
     """logZ, its batch mean and the four parameter gradients: within 1e-4 relative of the reference's
