@@ -40,7 +40,7 @@ def load():
     lib.hsmm_viterbi_workspace_bytes.argtypes = [i, i, i, i]
     lib.hsmm_logz_saved_bytes.restype = sz
     lib.hsmm_logz_saved_bytes.argtypes = [i, i, i, i, i]
-    lib.hsmm_emission.argtypes = [p, p, p, p, f, p, p, i, i, i, i, i, p, p, p, p, p]
+    lib.hsmm_emission.argtypes = [p, p, p, p, p, p, p, i, i, i, i, i, p, p, p, p, p]
     lib.hsmm_emission_workspace_bytes.restype = sz
     lib.hsmm_emission_workspace_bytes.argtypes = [i, i]
     lib.hsmm_viterbi.argtypes = [p, i, p, p, p, p, p, p, p, p, p, i, i, i, i, p, p, p, p, p]

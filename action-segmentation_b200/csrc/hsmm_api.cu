@@ -42,10 +42,10 @@ static int num_sms() {
 bool dp_reg_supported(int C, int L, int mode, bool sparse, bool xp);
 const char* dp_reg_name(int C, int L, int mode, bool sparse, bool xp);
 int dp_reg_launch(DpParams p, int mode, cudaStream_t st);
-int launch_emission(const float*, const float*, const float*, const float*, float, const float*, const int32_t*, int, int, int,
+int launch_emission(const float*, const float*, const float*, const float*, const float*, const float*, const int32_t*, int, int, int,
                     int, int, float*, float*, double*, cudaStream_t);
 size_t emission_tc_workspace_bytes(int D, int C);
-int launch_emission_tc(const float*, const float*, const float*, const float*, float, const float*, const int32_t*, int, int,
+int launch_emission_tc(const float*, const float*, const float*, const float*, const float*, const float*, const int32_t*, int, int,
                        int, int, int, float*, float*, double*, void*, int, cudaStream_t);
 int launch_weighted_sums(const float*, const float*, int, const int32_t*, int, int, int, int, float*, float*, int, cudaStream_t);
 int launch_moments(const float*, const int32_t*, int, int, int, double*, double*, int, cudaStream_t);
@@ -128,10 +128,10 @@ size_t hsmm_logz_saved_bytes(int B, int Tmax, int C, int K, int flags) {
     return saved_bytes(B, Tmax, C, (flags & HSMM_FLAG_F64_STATE) != 0);
 }
 
-int hsmm_emission(const float* X, const float* w, const float* bias, const float* inv_var, float row_const,
+int hsmm_emission(const float* X, const float* w, const float* bias, const float* inv_var, const float* row_const,
                   const float* penalty, const int32_t* lengths, int B, int Tmax, int D, int C, int ldc, float* em,
                   float* rowterm, double* offset, void* workspace, void* stream) {
-    if (!X || !w || !bias || !inv_var || !lengths || !em || !rowterm || !offset) {
+    if (!X || !w || !bias || !inv_var || !row_const || !lengths || !em || !rowterm || !offset) {
         set_error("hsmm_emission: null pointer");
         return HSMM_ERR_ARG;
     }

@@ -17,7 +17,7 @@ constexpr int E_THREADS = 256;
 
 __global__ void __launch_bounds__(E_THREADS)
 emission_kernel(const float* __restrict__ X, const float* __restrict__ w, const float* __restrict__ bias,
-                const float* __restrict__ inv_var, float row_const, const float* __restrict__ penalty,
+                const float* __restrict__ inv_var, const float* __restrict__ row_const_p, const float* __restrict__ penalty,
                 const int32_t* __restrict__ lengths, int Tmax, int D, int C, int ldc, int cs,
                 float* __restrict__ em, float* __restrict__ rowterm, double* __restrict__ offset) {
     extern __shared__ float sm[];
@@ -28,6 +28,7 @@ emission_kernel(const float* __restrict__ X, const float* __restrict__ w, const 
     float* Rs = Os + E_TF * cs;           // [E_TF] row terms
     __shared__ double red[E_THREADS / 32];
 
+    const float row_const = __ldg(row_const_p);
     const int b = blockIdx.y;
     const int t0 = blockIdx.x * E_TF;
     const int T = lengths[b];
@@ -163,7 +164,7 @@ emission_kernel(const float* __restrict__ X, const float* __restrict__ w, const 
     }
 }
 
-int launch_emission(const float* X, const float* w, const float* bias, const float* inv_var, float row_const,
+int launch_emission(const float* X, const float* w, const float* bias, const float* inv_var, const float* row_const,
                     const float* penalty, const int32_t* lengths, int B, int Tmax, int D, int C, int ldc,
                     float* em, float* rowterm, double* offset, cudaStream_t st) {
     cudaError_t e = cudaMemsetAsync(offset, 0, sizeof(double) * B, st);
@@ -191,56 +192,144 @@ int launch_emission(const float* X, const float* w, const float* bias, const flo
 }
 
 // ---------------------------------------------------------------------------------------------
-// Class-weighted feature sums: out_wx[c][d] += sum_f wgt[f][c] x[f][d]
-// persistent CTAs over tiles of W_TF frames; thread <-> feature dim, class accumulators in registers
+// Class-weighted feature sums: out_wx[c][d] += sum_f wgt[f][c] x[f][d]   (a (C x F).(F x D) contraction)
+//
+// Persistent CTAs over tiles of W_TF consecutive frames of one video.  Thread = (4 feature dims, frame
+// phase): it streams its float4 of x straight from global memory (a warp reads 512 contiguous bytes of
+// a frame; W_UNROLL loads in flight per thread), takes the CP class weights of the frame as broadcast
+// reads from shared memory and keeps a CP x 4 accumulator tile in registers across ALL its tiles; the
+// four frame phases are reduced through shared memory at the end and flushed with one atomic per entry.
 // ---------------------------------------------------------------------------------------------
-constexpr int W_TF = 32;
-constexpr int W_CB = 32;
-constexpr int W_THREADS = 256;
+constexpr int W_TF = 64;       // frames per tile
+constexpr int W_PH = 4;        // frame phases (thread groups working on different frames of the tile)
+constexpr int W_DQ = 64;       // float4 columns per CTA (256 feature dims)
+constexpr int W_THREADS = W_PH * W_DQ;
+constexpr int W_UNROLL = 8;
 
+template <int CP>
 __global__ void __launch_bounds__(W_THREADS)
 weighted_sums_kernel(const float* __restrict__ X, const float* __restrict__ wgt, int ldc,
                      const int32_t* __restrict__ lengths, int B, int Tmax, int D, int C, int tiles_per_video,
                      float* __restrict__ out_wx, float* __restrict__ out_wsum) {
-    __shared__ float Ws[W_TF][W_CB + 1];
+    __shared__ __align__(16) float Ws[W_TF][CP];
+    const int tid = threadIdx.x;
+    const int dq = tid & (W_DQ - 1), ph = tid / W_DQ;
+    const int d0 = blockIdx.y * (W_DQ * 4) + dq * 4;  // first feature dim of this thread
+    const int cb = blockIdx.z * CP;                   // first class of this CTA
+    const int nc = min(CP, C - cb);
+    const bool dok = d0 < D;                          // D % 4 == 0 on this path
+    const int ntiles = B * tiles_per_video;
+
+    float acc[CP][4];
+#pragma unroll
+    for (int c = 0; c < CP; ++c) acc[c][0] = acc[c][1] = acc[c][2] = acc[c][3] = 0.0f;
+    float wsum = 0.0f;  // thread c < nc (of the d-block 0 CTAs) accumulates the column sums
+
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int b = tile / tiles_per_video;
+        const int t0 = (tile - b * tiles_per_video) * W_TF;
+        const int T = lengths[b];
+        if (t0 >= T) continue;
+        const int nf = min(W_TF, T - t0);
+        __syncthreads();
+        for (int i = tid; i < W_TF * CP; i += W_THREADS) {
+            const int f = i / CP, c = i - f * CP;
+            Ws[f][c] = (f < nf && c < nc) ? __ldg(wgt + ((size_t)b * Tmax + t0 + f) * ldc + cb + c) : 0.0f;
+        }
+        __syncthreads();
+        if (blockIdx.y == 0 && tid < nc) {
+            for (int f = 0; f < nf; ++f) wsum += Ws[f][tid];
+        }
+        if (dok) {
+            const float* xp = X + ((size_t)b * Tmax + t0) * D + d0;
+#pragma unroll
+            for (int f0 = 0; f0 < W_TF / W_PH; f0 += W_UNROLL) {
+                float4 x[W_UNROLL];
+#pragma unroll
+                for (int u = 0; u < W_UNROLL; ++u) {
+                    const int f = (f0 + u) * W_PH + ph;
+                    x[u] = (f < nf) ? __ldg(reinterpret_cast<const float4*>(xp + (size_t)f * D)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int u = 0; u < W_UNROLL; ++u) {
+                    const int f = (f0 + u) * W_PH + ph;
+#pragma unroll
+                    for (int c4 = 0; c4 < CP / 4; ++c4) {
+                        const float4 w = *reinterpret_cast<const float4*>(&Ws[f][c4 * 4]);
+                        const float wv[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            acc[c4 * 4 + q][0] = fmaf(wv[q], x[u].x, acc[c4 * 4 + q][0]);
+                            acc[c4 * 4 + q][1] = fmaf(wv[q], x[u].y, acc[c4 * 4 + q][1]);
+                            acc[c4 * 4 + q][2] = fmaf(wv[q], x[u].z, acc[c4 * 4 + q][2]);
+                            acc[c4 * 4 + q][3] = fmaf(wv[q], x[u].w, acc[c4 * 4 + q][3]);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    // reduce the frame phases through shared memory (one class at a time), then one atomic per entry
+    __shared__ __align__(16) float Red[W_PH][W_DQ * 4];
+#pragma unroll
+    for (int c = 0; c < CP; ++c) {
+        __syncthreads();
+        *reinterpret_cast<float4*>(&Red[ph][dq * 4]) = make_float4(acc[c][0], acc[c][1], acc[c][2], acc[c][3]);
+        __syncthreads();
+        if (c < nc && tid < W_DQ * 4) {
+            const int d = blockIdx.y * (W_DQ * 4) + tid;
+            if (d < D) {
+                const float v = (Red[0][tid] + Red[1][tid]) + (Red[2][tid] + Red[3][tid]);
+                atomicAdd(out_wx + (size_t)(cb + c) * D + d, v);
+            }
+        }
+    }
+    if (blockIdx.y == 0 && tid < nc) atomicAdd(out_wsum + cb + tid, wsum);
+}
+
+// generic fallback (D % 4 != 0 or unaligned X): thread <-> feature dim, scalar loads
+__global__ void __launch_bounds__(256)
+weighted_sums_generic_kernel(const float* __restrict__ X, const float* __restrict__ wgt, int ldc,
+                             const int32_t* __restrict__ lengths, int B, int Tmax, int D, int C, int tiles_per_video,
+                             float* __restrict__ out_wx, float* __restrict__ out_wsum) {
+    constexpr int TF = 32, CB = 16;
+    __shared__ float Ws[TF][CB + 1];
     const int tid = threadIdx.x;
     const int ntiles = B * tiles_per_video;
-    for (int cb = 0; cb < C; cb += W_CB) {
-        const int nc = min(W_CB, C - cb);
-        for (int d0 = 0; d0 < D; d0 += W_THREADS) {
+    for (int cb = 0; cb < C; cb += CB) {
+        const int nc = min(CB, C - cb);
+        for (int d0 = 0; d0 < D; d0 += 256) {
             const int d = d0 + tid;
-            float acc[W_CB];
+            float acc[CB];
 #pragma unroll
-            for (int c = 0; c < W_CB; ++c) acc[c] = 0.0f;
-            float wsum = 0.0f;  // thread c < nc accumulates column sums (first d-pass only)
+            for (int c = 0; c < CB; ++c) acc[c] = 0.0f;
+            float wsum = 0.0f;
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 const int b = tile / tiles_per_video;
-                const int t0 = (tile - b * tiles_per_video) * W_TF;
+                const int t0 = (tile - b * tiles_per_video) * TF;
                 const int T = lengths[b];
                 if (t0 >= T) continue;
-                const int nf = min(W_TF, T - t0);
+                const int nf = min(TF, T - t0);
                 __syncthreads();
-                for (int i = tid; i < W_TF * W_CB; i += W_THREADS) {
-                    const int f = i / W_CB, c = i - f * W_CB;
+                for (int i = tid; i < TF * CB; i += 256) {
+                    const int f = i / CB, c = i - f * CB;
                     Ws[f][c] = (f < nf && c < nc) ? __ldg(wgt + ((size_t)b * Tmax + t0 + f) * ldc + cb + c) : 0.0f;
                 }
                 __syncthreads();
-                if (d0 == 0 && tid < nc) {
+                if (d0 == 0 && tid < nc)
                     for (int f = 0; f < nf; ++f) wsum += Ws[f][tid];
-                }
                 if (d < D) {
                     const float* xp = X + ((size_t)b * Tmax + t0) * D + d;
-#pragma unroll 4
-                    for (int f = 0; f < W_TF; ++f) {
-                        const float x = (f < nf) ? __ldg(xp + (size_t)f * D) : 0.0f;
+                    for (int f = 0; f < nf; ++f) {
+                        const float x = __ldg(xp + (size_t)f * D);
 #pragma unroll
-                        for (int c = 0; c < W_CB; ++c) acc[c] = fmaf(Ws[f][c], x, acc[c]);
+                        for (int c = 0; c < CB; ++c) acc[c] = fmaf(Ws[f][c], x, acc[c]);
                     }
                 }
             }
             if (d < D) {
 #pragma unroll
-                for (int c = 0; c < W_CB; ++c)
+                for (int c = 0; c < CB; ++c)
                     if (c < nc) atomicAdd(out_wx + (size_t)(cb + c) * D + d, acc[c]);
             }
             if (d0 == 0 && tid < nc) atomicAdd(out_wsum + cb + tid, wsum);
@@ -250,11 +339,28 @@ weighted_sums_kernel(const float* __restrict__ X, const float* __restrict__ wgt,
 
 int launch_weighted_sums(const float* X, const float* wgt, int ldc, const int32_t* lengths, int B, int Tmax, int D, int C,
                          float* out_wx, float* out_wsum, int num_sms, cudaStream_t st) {
+    if (D % 4 != 0 || (reinterpret_cast<uintptr_t>(X) & 15)) {
+        const int tpv = (Tmax + 31) / 32;
+        int grid = num_sms * 4;
+        if (grid > B * tpv) grid = B * tpv;
+        if (grid < 1) grid = 1;
+        weighted_sums_generic_kernel<<<grid, 256, 0, st>>>(X, wgt, ldc, lengths, B, Tmax, D, C, tpv, out_wx, out_wsum);
+        return check_launch("weighted_sums_generic_kernel");
+    }
     const int tiles_per_video = (Tmax + W_TF - 1) / W_TF;
-    int grid = num_sms * 4;
-    if (grid > B * tiles_per_video) grid = B * tiles_per_video;
-    if (grid < 1) grid = 1;
-    weighted_sums_kernel<<<grid, W_THREADS, 0, st>>>(X, wgt, ldc, lengths, B, Tmax, D, C, tiles_per_video, out_wx, out_wsum);
+    const int dblocks = (D + W_DQ * 4 - 1) / (W_DQ * 4);
+    const int cp = C <= 8 ? 8 : (C <= 16 ? 16 : (C <= 24 ? 24 : 32));
+    const int cblocks = (C + cp - 1) / cp;
+    int gx = (num_sms * (cp <= 16 ? 2 : 1)) / (dblocks * cblocks);  // resident CTAs: 203-246 registers at CP >= 24
+    if (gx < 1) gx = 1;
+    if (gx > B * tiles_per_video) gx = B * tiles_per_video;
+    dim3 grid(gx, dblocks, cblocks);
+    switch (cp) {
+        case 8: weighted_sums_kernel<8><<<grid, W_THREADS, 0, st>>>(X, wgt, ldc, lengths, B, Tmax, D, C, tiles_per_video, out_wx, out_wsum); break;
+        case 16: weighted_sums_kernel<16><<<grid, W_THREADS, 0, st>>>(X, wgt, ldc, lengths, B, Tmax, D, C, tiles_per_video, out_wx, out_wsum); break;
+        case 24: weighted_sums_kernel<24><<<grid, W_THREADS, 0, st>>>(X, wgt, ldc, lengths, B, Tmax, D, C, tiles_per_video, out_wx, out_wsum); break;
+        default: weighted_sums_kernel<32><<<grid, W_THREADS, 0, st>>>(X, wgt, ldc, lengths, B, Tmax, D, C, tiles_per_video, out_wx, out_wsum); break;
+    }
     return check_launch("weighted_sums_kernel");
 }
 

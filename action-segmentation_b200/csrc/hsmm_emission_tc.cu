@@ -113,7 +113,7 @@ struct Params {
     float* em;
     float* rowterm;
     double* offset;
-    float row_const;
+    const float* row_const;  // device scalar
     int B, Tmax, D, C, ldc;
     int npad;     // classes padded to a multiple of 16 (UMMA N)
     int nchunk;   // ceil(D / 32)
@@ -258,6 +258,7 @@ emission_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
         const int q = warp & 3;              // TMEM lane quarter this warp may read
         const int r = q * 32 + lane;         // row inside the tile
         const long long total_rows = (long long)p.B * p.Tmax;
+        const float row_const = __ldg(p.row_const);
         int st = 0;
         uint32_t ph = 0;
         int acc = 0;
@@ -315,7 +316,7 @@ emission_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
                         }
                         v[c] = o;
                     }
-                    rt = (-0.5f * rowsq + p.row_const) + m;
+                    rt = (-0.5f * rowsq + row_const) + m;
                     contrib = (double)rt;
                 } else {
 #pragma unroll
@@ -468,7 +469,7 @@ size_t emission_tc_workspace_bytes(int D, int C) {
 }
 
 // returns 1 when the shape / alignment is not eligible (caller falls back to the SIMT kernel), 0 on launch, < 0 on error
-int launch_emission_tc(const float* X, const float* w, const float* bias, const float* inv_var, float row_const,
+int launch_emission_tc(const float* X, const float* w, const float* bias, const float* inv_var, const float* row_const,
                        const float* penalty, const int32_t* lengths, int B, int Tmax, int D, int C, int ldc, float* em,
                        float* rowterm, double* offset, void* workspace, int num_sms, cudaStream_t st) {
     using namespace etc;

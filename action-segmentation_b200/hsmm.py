@@ -71,11 +71,11 @@ def emission_params(means, cov_diag):
     w = means * inv_var
     bias = -0.5 * (means * w).sum(dim=1)
     D = means.shape[1]
-    row_const = float(-0.5 * torch.log(cov_diag.double()).sum() - 0.5 * D * LOG_2PI)
+    row_const = (-0.5 * torch.log(cov_diag.double()).sum() - 0.5 * D * LOG_2PI).to(torch.float32).reshape(1)  # stays on device
     return w, bias, inv_var, row_const
 
 
-def emission_scores(features, means, cov_diag, penalty, lengths_i32, tensor_cores=True):
+def emission_scores(features, means, cov_diag, penalty, lengths_i32, tensor_cores=True, params=None):
     """hsmm_emission: returns (em (B,T,ldc), rowterm (B,T), offset (B) float64).  `tensor_cores=False` withholds
     the workspace, which selects the SIMT kernel (used by the tests to compare the two)."""
     _need_cuda(features, means, cov_diag, penalty, lengths_i32)
@@ -84,7 +84,7 @@ def emission_scores(features, means, cov_diag, penalty, lengths_i32, tensor_core
     C = means.shape[0]
     ldc = ldc_of(C)
     X = _f32(features)
-    w, bias, inv_var, row_const = emission_params(_f32(means), _f32(cov_diag))
+    w, bias, inv_var, row_const = emission_params(_f32(means), _f32(cov_diag)) if params is None else params
     w, bias, inv_var = w.contiguous(), bias.contiguous(), inv_var.contiguous()
     pen = _f32(penalty)
     if pen is not None and tuple(pen.shape) != (B, T, C):
@@ -94,7 +94,7 @@ def emission_scores(features, means, cov_diag, penalty, lengths_i32, tensor_core
     offset = torch.empty(B, device=X.device, dtype=torch.float64)
     ws_bytes = lib.hsmm_emission_workspace_bytes(D, C) if tensor_cores else 0
     ws = torch.empty(ws_bytes, device=X.device, dtype=torch.uint8) if ws_bytes else None
-    _lib.check(lib.hsmm_emission(_p(X), _p(w), _p(bias), _p(inv_var), row_const, _p(pen), _p(lengths_i32), B, T, D, C, ldc,
+    _lib.check(lib.hsmm_emission(_p(X), _p(w), _p(bias), _p(inv_var), _p(row_const), _p(pen), _p(lengths_i32), B, T, D, C, ldc,
                                  _p(em), _p(rowterm), _p(offset), _p(ws), _stream()), "hsmm_emission")
     return em, rowterm, offset
 

@@ -123,6 +123,8 @@ def make_task(t, steps, V, D, K, tmin, tmax, narration, gen, device):
     tk.lengths_i32, tk.order = hsmm.prepare_lengths(tk.lengths, torch.device(device))
     tk.frames = int(tk.lengths.sum())
     tk.class_ids = torch.arange(C + 1, device=device, dtype=torch.int32)
+    tk.gradw = torch.full((V,), 1.0 / V, device=device)
+    tk.eparams = hsmm.emission_params(tk.means, tk.cov_diag)  # w, bias, 1/var, row constant (parameter-only work)
     # ordering constraints leave <= 2 unmasked transitions per class: hint for the sparse-transition kernels
     tk.pred, tk.succ = hsmm.sparse_transition_lists(~tmask, torch.device(device))
     return tk
@@ -148,40 +150,51 @@ def packed_layout(tasks):
 # one step of the hot path, inputs resident in HBM, library kernels only
 # ---------------------------------------------------------------------------------------------
 def device_step(tasks, streams, packed, layout, world):
+    """Every task: emission -> {forward -> backward -> weighted sums} and, concurrently on a second stream,
+    Viterbi (which needs the emission scores only)."""
     from action_segmentation_b200 import hsmm
-    import ctypes
     lib = hsmm._lib.load()
     cur = torch.cuda.current_stream()
     packed.zero_()
     fork = torch.cuda.Event()
     fork.record(cur)
     outs = []
+    n = len(tasks)
     for i, tk in enumerate(tasks):
-        st = streams[i % len(streams)]
+        st, st2 = streams[i], streams[n + i]
         st.wait_event(fork)
         with torch.cuda.stream(st):
             off, sizes = layout[i]
             v = []
             o = off
-            for n in sizes:
-                v.append(packed[o:o + n])
-                o += n
+            for m in sizes:
+                v.append(packed[o:o + m])
+                o += m
             wx, d_trans, d_len, d_init, wsum, lz = v
-            em, rowterm, offset = hsmm.emission_scores(tk.X, tk.means, tk.cov_diag, tk.penalty, tk.lengths_i32)
+            em, rowterm, offset = hsmm.emission_scores(tk.X, tk.means, tk.cov_diag, tk.penalty, tk.lengths_i32,
+                                                       params=tk.eparams)
+            em_ready = torch.cuda.Event()
+            em_ready.record(st)
+        with torch.cuda.stream(st2):
+            st2.wait_event(em_ready)
+            spans, labels, score = hsmm.viterbi_decode(em, tk.C, tk.init, tk.trans, tk.lenp, tk.end, offset, tk.lengths_i32,
+                                                       tk.order, tk.class_ids, want_labels=True, want_score=False,
+                                                       trans_pred=tk.pred)
+            em.record_stream(st2)
+            offset.record_stream(st2)
+            outs.append((spans, labels))
+        with torch.cuda.stream(st):
+            xp = tk.penalty is not None
             logz, saved = hsmm.logz_forward(em, tk.C, tk.init, tk.trans, tk.lenp, tk.end, offset, tk.lengths_i32, tk.order,
-                                            trans_pred=tk.pred)
-            g = torch.full((tk.V,), 1.0 / (tk.V * world), device=em.device)
+                                            trans_pred=tk.pred, f64_state=xp)
+            g = tk.gradw if world == 1 else tk.gradw / world
             _, _, _, d_em = hsmm.logz_backward(em, tk.C, tk.init, tk.trans, tk.lenp, tk.end, tk.lengths_i32, tk.order, g,
                                                saved, out=(d_init, d_trans.view(tk.C, tk.C), d_len.view(tk.K, tk.C)),
-                                               trans_succ=tk.succ)
+                                               trans_succ=tk.succ, f64_state=xp)
             hsmm._lib.check(lib.hsmm_weighted_feature_sums(hsmm._p(tk.X), hsmm._p(d_em), d_em.shape[2], hsmm._p(tk.lengths_i32),
                                                            tk.V, tk.Tmax, tk.D, tk.C, hsmm._p(wx), hsmm._p(wsum),
                                                            hsmm._stream()), "hsmm_weighted_feature_sums")
             lz.copy_(logz.sum().float().reshape(1))
-            spans, labels, score = hsmm.viterbi_decode(em, tk.C, tk.init, tk.trans, tk.lenp, tk.end, offset, tk.lengths_i32,
-                                                       tk.order, tk.class_ids, want_labels=True, want_score=False,
-                                                       trans_pred=tk.pred)
-            outs.append((spans, labels))
     for st in streams:
         ev = torch.cuda.Event()
         ev.record(st)
@@ -254,12 +267,15 @@ def kernel_breakdown(tasks, reps=2):
 
     for _ in range(reps):
         for tk in tasks:
-            em, rowterm, offset = timed("emission", lambda: hsmm.emission_scores(tk.X, tk.means, tk.cov_diag, tk.penalty, tk.lengths_i32))
+            em, rowterm, offset = timed("emission", lambda: hsmm.emission_scores(tk.X, tk.means, tk.cov_diag, tk.penalty, tk.lengths_i32,
+                                                                                    params=tk.eparams))
+            xp = tk.penalty is not None
             logz, saved = timed("logz_forward", lambda: hsmm.logz_forward(em, tk.C, tk.init, tk.trans, tk.lenp, tk.end, offset,
-                                                                          tk.lengths_i32, tk.order, trans_pred=tk.pred))
+                                                                          tk.lengths_i32, tk.order, trans_pred=tk.pred,
+                                                                          f64_state=xp))
             g = torch.full((tk.V,), 1.0 / tk.V, device=em.device)
             d = timed("logz_backward", lambda: hsmm.logz_backward(em, tk.C, tk.init, tk.trans, tk.lenp, tk.end, tk.lengths_i32,
-                                                                  tk.order, g, saved, trans_succ=tk.succ))
+                                                                  tk.order, g, saved, trans_succ=tk.succ, f64_state=xp))
             timed("weighted_feature_sums", lambda: hsmm.weighted_feature_sums(tk.X, d[3], tk.C, tk.lengths_i32))
             timed("viterbi", lambda: hsmm.viterbi_decode(em, tk.C, tk.init, tk.trans, tk.lenp, tk.end, offset, tk.lengths_i32,
                                                          tk.order, tk.class_ids, want_score=False, trans_pred=tk.pred))
@@ -385,7 +401,7 @@ def main():
     frames = sum(tk.frames for tk in tasks)
     layout, total = packed_layout(tasks)
     packed = torch.zeros(total, device=device)
-    streams = [torch.cuda.Stream() for _ in range(len(tasks))]
+    streams = [torch.cuda.Stream() for _ in range(2 * len(tasks))]
 
     def barrier():
         torch.cuda.synchronize()

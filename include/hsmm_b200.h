@@ -75,7 +75,8 @@ const char* hsmm_last_error(void);
  *   offset[b]  = sum_{t < lengths[b]} rowterm[b,t]   (double; added to logZ / Viterbi scores)
  * Frames t >= lengths[b] get em = 0, rowterm = 0.
  *
- * X (B,Tmax,D); w (C,D); bias (C); inv_var (D); penalty (B,Tmax,C) or NULL;
+ * X (B,Tmax,D); w (C,D); bias (C); inv_var (D); row_const: DEVICE pointer to one float (so that the caller never
+ * synchronises to build it); penalty (B,Tmax,C) or NULL;
  * em (B,Tmax,ldc) out; rowterm (B,Tmax) out; offset (B) out (double, overwritten).
  * workspace: hsmm_emission_workspace_bytes(D, C) bytes (16-byte aligned) or NULL.  With a workspace and an
  * eligible shape (C <= 64, D % 4 == 0, X 16-byte aligned) the contraction runs on the tensor cores
@@ -83,7 +84,7 @@ const char* hsmm_last_error(void);
  * SIMT fp32 kernel.  hsmm_emission_workspace_bytes returns 0 for shapes without a tensor-core plan.
  */
 size_t hsmm_emission_workspace_bytes(int D, int C);
-int hsmm_emission(const float* X, const float* w, const float* bias, const float* inv_var, float row_const,
+int hsmm_emission(const float* X, const float* w, const float* bias, const float* inv_var, const float* row_const,
                   const float* penalty, const int32_t* lengths, int B, int Tmax, int D, int C, int ldc,
                   float* em, float* rowterm, double* offset, void* workspace, void* stream);
 

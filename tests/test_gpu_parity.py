@@ -268,6 +268,31 @@ def test_sparse_hint_degenerate_falls_back_to_dense(C, K):
     assert np.allclose(lz_d.cpu().numpy(), ref_logz, rtol=1e-6)
 
 
+@pytest.mark.parametrize("B,Tmax,D,C", [(6, 333, 200, 23), (5, 200, 200, 7), (3, 150, 64, 48), (2, 90, 300, 13), (4, 77, 6, 5),
+                                        (2, 130, 200, 133)])
+def test_weighted_feature_sums_vs_numpy(B, Tmax, D, C):
+    """hsmm_weighted_feature_sums (the reduction behind d/d gaussian_means and the supervised class means,
+    semimarkov_utils.py:74-126) against a float64 numpy contraction."""
+    import action_segmentation_b200 as pkg
+    rng = np.random.default_rng(B + Tmax + D + C)
+    lengths = rng.integers(1, Tmax + 1, size=B)
+    lengths[0] = Tmax
+    X = rng.normal(size=(B, Tmax, D)).astype(np.float32)
+    ldc = pkg.hsmm.ldc_of(C)
+    wgt = np.zeros((B, Tmax, ldc), dtype=np.float32)
+    wgt[:, :, :C] = rng.dirichlet(np.ones(C), size=(B, Tmax))
+    li = torch.from_numpy(lengths).to(torch.int32).cuda()
+    wx, wsum = pkg.hsmm.weighted_feature_sums(torch.from_numpy(X).cuda(), torch.from_numpy(wgt).cuda(), C, li)
+    ref_wx = np.zeros((C, D))
+    ref_ws = np.zeros(C)
+    for b, T in enumerate(lengths):
+        ref_wx += wgt[b, :T, :C].astype(np.float64).T @ X[b, :T].astype(np.float64)
+        ref_ws += wgt[b, :T, :C].astype(np.float64).sum(axis=0)
+    scale = np.sqrt(float(lengths.sum()))  # typical magnitude of a sum of ~N(0, w^2) terms
+    assert np.abs(wx.cpu().numpy() - ref_wx).max() < 2e-5 * scale
+    assert np.abs(wsum.cpu().numpy() - ref_ws).max() < 1e-5 * np.abs(ref_ws).max()
+
+
 def test_supervised_fit_golden(golden):
     """fit_supervised closed form (semimarkov_modules.py:195-256) against the reference's fitted parameters."""
     import action_segmentation_b200 as pkg
