@@ -150,39 +150,46 @@ def packed_layout(tasks):
 # one step of the hot path, inputs resident in HBM, library kernels only
 # ---------------------------------------------------------------------------------------------
 def device_step(tasks, streams, packed, layout, world):
-    """Every task: emission -> {forward -> backward -> weighted sums} and, concurrently on a second stream,
-    Viterbi (which needs the emission scores only)."""
+    """One pass of the hot path over every task's batch, scheduled in three phases because the two streaming
+    kernels are persistent one-CTA-per-SM kernels that cannot share an SM with resident DP CTAs:
+      A  emission scoring of every task (tensor cores, back to back on one stream);
+      B  per task, on its own streams: forward -> backward and, concurrently, Viterbi (latency-bound DP
+         kernels: all tasks in flight together);
+      C  class-weighted feature sums of every task (d/d means) once the backward passes are done."""
     from action_segmentation_b200 import hsmm
     lib = hsmm._lib.load()
     cur = torch.cuda.current_stream()
     packed.zero_()
     fork = torch.cuda.Event()
     fork.record(cur)
-    outs = []
     n = len(tasks)
+    s_stream = streams[2 * n]
+    s_stream.wait_event(fork)
+    ems = []
+    with torch.cuda.stream(s_stream):
+        for tk in tasks:
+            ems.append(hsmm.emission_scores(tk.X, tk.means, tk.cov_diag, tk.penalty, tk.lengths_i32, params=tk.eparams))
+        em_done = torch.cuda.Event()
+        em_done.record(s_stream)
+    outs, views, dems, bwd_done = [], [], [], []
     for i, tk in enumerate(tasks):
         st, st2 = streams[i], streams[n + i]
-        st.wait_event(fork)
-        with torch.cuda.stream(st):
-            off, sizes = layout[i]
-            v = []
-            o = off
-            for m in sizes:
-                v.append(packed[o:o + m])
-                o += m
-            wx, d_trans, d_len, d_init, wsum, lz = v
-            em, rowterm, offset = hsmm.emission_scores(tk.X, tk.means, tk.cov_diag, tk.penalty, tk.lengths_i32,
-                                                       params=tk.eparams)
-            em_ready = torch.cuda.Event()
-            em_ready.record(st)
+        em, rowterm, offset = ems[i]
+        off, sizes = layout[i]
+        v = []
+        o = off
+        for m in sizes:
+            v.append(packed[o:o + m])
+            o += m
+        wx, d_trans, d_len, d_init, wsum, lz = v
+        views.append((wx, wsum, lz))
+        st2.wait_event(em_done)
         with torch.cuda.stream(st2):
-            st2.wait_event(em_ready)
             spans, labels, score = hsmm.viterbi_decode(em, tk.C, tk.init, tk.trans, tk.lenp, tk.end, offset, tk.lengths_i32,
                                                        tk.order, tk.class_ids, want_labels=True, want_score=False,
                                                        trans_pred=tk.pred)
-            em.record_stream(st2)
-            offset.record_stream(st2)
             outs.append((spans, labels))
+        st.wait_event(em_done)
         with torch.cuda.stream(st):
             xp = tk.penalty is not None
             logz, saved = hsmm.logz_forward(em, tk.C, tk.init, tk.trans, tk.lenp, tk.end, offset, tk.lengths_i32, tk.order,
@@ -191,10 +198,24 @@ def device_step(tasks, streams, packed, layout, world):
             _, _, _, d_em = hsmm.logz_backward(em, tk.C, tk.init, tk.trans, tk.lenp, tk.end, tk.lengths_i32, tk.order, g,
                                                saved, out=(d_init, d_trans.view(tk.C, tk.C), d_len.view(tk.K, tk.C)),
                                                trans_succ=tk.succ, f64_state=xp)
+            lz.copy_(logz.sum().float().reshape(1))
+            dems.append(d_em)
+            ev = torch.cuda.Event()
+            ev.record(st)
+            bwd_done.append(ev)
+    sched = os.environ.get("HSMM_BENCH_SCHED", "chain")
+    for i, (tk, d_em, (wx, wsum, lz)) in enumerate(zip(tasks, dems, views)):
+        if sched == "phases":  # every weighted sum after every backward pass, on one stream
+            if i == 0:
+                for ev in bwd_done:
+                    s_stream.wait_event(ev)
+            ws = s_stream
+        else:                  # each task's weighted sum right behind its backward pass
+            ws = streams[i]
+        with torch.cuda.stream(ws):
             hsmm._lib.check(lib.hsmm_weighted_feature_sums(hsmm._p(tk.X), hsmm._p(d_em), d_em.shape[2], hsmm._p(tk.lengths_i32),
                                                            tk.V, tk.Tmax, tk.D, tk.C, hsmm._p(wx), hsmm._p(wsum),
                                                            hsmm._stream()), "hsmm_weighted_feature_sums")
-            lz.copy_(logz.sum().float().reshape(1))
     for st in streams:
         ev = torch.cuda.Event()
         ev.record(st)
@@ -401,7 +422,7 @@ def main():
     frames = sum(tk.frames for tk in tasks)
     layout, total = packed_layout(tasks)
     packed = torch.zeros(total, device=device)
-    streams = [torch.cuda.Stream() for _ in range(2 * len(tasks))]
+    streams = [torch.cuda.Stream() for _ in range(2 * len(tasks) + 1)]
 
     def barrier():
         torch.cuda.synchronize()
