@@ -58,8 +58,12 @@ def sparse_transition_lists(allowed, device):
 
 
 def prepare_lengths(lengths, device):
-    """int32 device lengths + processing order (longest first) for load balance."""
-    lengths_dev = lengths.to(device=device, dtype=torch.int32).contiguous()
+    """int32 device lengths + processing order (longest first) for load balance.  Host lengths go through
+    pinned memory so that the copy never synchronises with earlier work on the stream."""
+    if lengths.is_cuda:
+        lengths_dev = lengths.to(device=device, dtype=torch.int32).contiguous()
+    else:
+        lengths_dev = lengths.to(torch.int32).contiguous().pin_memory().to(device, non_blocking=True)
     order = torch.argsort(lengths_dev, descending=True, stable=True).to(torch.int32).contiguous()
     return lengths_dev, order
 

@@ -102,12 +102,14 @@ class SemiMarkovModule(nn.Module):
         pass
 
     def remove_transition_constraints(self):
+        self.__dict__['_sparse_cache'] = {}
         self.transition_constraints = None
         self.init_constraints = None
         self.allowed_ends = None
 
     def set_transition_constraints(self, allowed_starts, allowed_transitions, allowed_ends):
         # semimarkov_modules.py:169-193
+        self.__dict__['_sparse_cache'] = {}
         init_c = torch.full((self.n_classes,), 1, dtype=torch.bool)
         assert all(x >= 0 for x in allowed_starts)
         init_c[torch.LongTensor(list(sorted(allowed_starts)))] = 0
@@ -222,14 +224,34 @@ class SemiMarkovModule(nn.Module):
         # indexed [to_state, from_state]: each column is normalised
         return F.log_softmax(masked, dim=0)
 
+    def _task_cache(self, valid_classes, device):
+        """Index bookkeeping of one valid-class set (= one task, corpus.py:326-329), built once on the host and
+        kept on the device: class indices (merged for emission/length parameters), the local->global id table
+        for decoding, the sparse-transition hint.  No per-call host<->device synchronisation."""
+        vc_host = None if valid_classes is None else [int(x) for x in valid_classes.detach().cpu().tolist()]
+        key = (None if vc_host is None else tuple(vc_host), str(device))
+        cache = self.__dict__.setdefault('_sparse_cache', {})
+        if key not in cache:
+            ids = list(range(self.n_classes)) if vc_host is None else vc_host
+            merged = ids if self.merge_classes is None else [self.merge_classes[i] for i in ids]
+            allowed = None
+            if self.transition_constraints is not None:
+                allowed = ~self.transition_constraints.detach().cpu()
+                if vc_host is not None:
+                    vc = torch.as_tensor(vc_host, dtype=torch.long)
+                    allowed = allowed[vc][:, vc]
+                if not self.allow_self_transitions:
+                    allowed = allowed & ~torch.eye(allowed.shape[0], dtype=torch.bool)
+            cache[key] = dict(
+                ids_host=ids,
+                idx=None if vc_host is None else torch.as_tensor(ids, dtype=torch.long).to(device),
+                merged_idx=torch.as_tensor(merged, dtype=torch.long).to(device),
+                decode_ids=torch.as_tensor(ids + [self.n_classes], dtype=torch.int32).to(device),
+                sparse=None if allowed is None else hsmm.sparse_transition_lists(allowed, device))
+        return cache[key]
+
     def _class_indices(self, valid_classes, device):
-        if valid_classes is None:
-            idx = torch.arange(self.n_classes, device=device)
-        else:
-            idx = valid_classes.to(device)
-        if self.merge_classes is not None:
-            idx = torch.as_tensor([self.merge_classes[int(ix)] for ix in idx], dtype=torch.long, device=device)
-        return idx
+        return self._task_cache(valid_classes, device)['merged_idx']
 
     def _length_log_probs_with_rates(self, log_rates):
         # semimarkov_modules.py:383-398: Poisson(exp(log_rate)).log_prob(k), k = 0..max_k-1
@@ -272,37 +294,21 @@ class SemiMarkovModule(nn.Module):
     def set_z(self, features, lengths, use_mean=False):
         self.kl = torch.zeros(features.size(0), device=features.device, requires_grad=True)
 
-    def _end_scores(self, valid_classes, batch_size, additional_allowed_ends_per_instance, device):
-        """EOS row of log_hsmm's augmented transitions (semimarkov_modules.py:462-471, 566-577)."""
+    def _end_scores(self, ids_host, batch_size, additional_allowed_ends_per_instance, device):
+        """EOS row of log_hsmm's augmented transitions (semimarkov_modules.py:462-471, 566-577); built in pinned
+        host memory and copied asynchronously."""
         if self.allowed_ends is None:
             return None
-        if additional_allowed_ends_per_instance is None:
-            additional_allowed_ends_per_instance = [set() for _ in range(batch_size)]
-        vc = list(range(self.n_classes)) if valid_classes is None else [int(x) for x in valid_classes]
-        end = torch.full((batch_size, len(vc)), BIG_NEG)
-        for b, extra in enumerate(additional_allowed_ends_per_instance):
-            ok = set(self.allowed_ends) | set(int(x) for x in extra)
-            cols = [i for i, ix in enumerate(vc) if ix in ok]
-            assert cols, "no allowed end state among the valid classes"
-            end[b, cols] = 0.0
-        return end.to(device)
-
-    def _sparse_hint(self, valid_classes, device):
-        """Unmasked-transition lists for the kernels' sparse mode: with ordering constraints
-        (set_transition_constraints) at most a few entries per class survive the -1e9 mask."""
-        if self.transition_constraints is None:
-            return None
-        key = (None if valid_classes is None else tuple(int(x) for x in valid_classes), str(device))
-        cache = self.__dict__.setdefault('_sparse_cache', {})
-        if key not in cache:
-            allowed = ~self.transition_constraints.detach().cpu()
-            if valid_classes is not None:
-                vc = valid_classes.cpu()
-                allowed = allowed[vc][:, vc]
-            if not self.allow_self_transitions:
-                allowed = allowed & ~torch.eye(allowed.shape[0], dtype=torch.bool)
-            cache[key] = hsmm.sparse_transition_lists(allowed, device)
-        return cache[key]
+        base = torch.tensor([0.0 if ix in self.allowed_ends else BIG_NEG for ix in ids_host])
+        end = base.unsqueeze(0).repeat(batch_size, 1)
+        if additional_allowed_ends_per_instance is not None:
+            pos = {ix: i for i, ix in enumerate(ids_host)}
+            for b, extra in enumerate(additional_allowed_ends_per_instance):
+                for x in extra:
+                    if int(x) in pos:
+                        end[b, pos[int(x)]] = 0.0
+        assert bool((end == 0).any(dim=1).all()), "no allowed end state among the valid classes"
+        return end.pin_memory().to(device, non_blocking=True)
 
     def __getstate__(self):
         d = super().__getstate__() if hasattr(super(), '__getstate__') else dict(self.__dict__)
@@ -314,12 +320,11 @@ class SemiMarkovModule(nn.Module):
         dev = features.device
         if dev.type != 'cuda':
             raise HsmmError("the HSMM path runs on CUDA only (no CPU fallback); call .cuda() on the model and inputs")
-        if valid_classes is not None:
-            valid_classes = valid_classes.to(dev)
-        idx = self._class_indices(valid_classes, dev)
-        C = len(idx)
+        tc = self._task_cache(valid_classes, dev)
+        idx = tc['merged_idx']
+        C = len(tc['ids_host'])
         T = features.size(1)
-        lenp = self.length_log_probs(valid_classes)
+        lenp = self._length_log_probs_with_rates(self.poisson_log_rates[idx])
         K = lenp.size(0)
         if K > T:  # semimarkov_modules.py:450-452
             K = T
@@ -327,11 +332,11 @@ class SemiMarkovModule(nn.Module):
         if K < 2:
             raise HsmmError("padded batch length %d leaves no usable segment length" % T)
         lengths_i32, order = hsmm.prepare_lengths(lengths, dev)
-        end = self._end_scores(valid_classes, features.size(0), additional_allowed_ends_per_instance, dev)
+        end = self._end_scores(tc['ids_host'], features.size(0), additional_allowed_ends_per_instance, dev)
         return dict(means=self.gaussian_means[idx], cov_diag=torch.diagonal(self.gaussian_cov),
-                    init=self.initial_log_probs(valid_classes), trans=self.transition_log_probs(valid_classes),
-                    lenp=lenp, end=end, lengths_i32=lengths_i32, order=order, C=C, valid_classes=valid_classes,
-                    sparse=self._sparse_hint(valid_classes, dev))
+                    init=self.initial_log_probs(tc['idx']), trans=self.transition_log_probs(tc['idx']),
+                    lenp=lenp, end=end, lengths_i32=lengths_i32, order=order, C=C, valid_classes=tc['idx'],
+                    sparse=tc['sparse'], decode_ids=tc['decode_ids'])
 
     def score_features(self, features, lengths, valid_classes, add_eos, use_mean_z,
                        additional_allowed_ends_per_instance=None, constraints=None, return_elp=False):
@@ -344,6 +349,7 @@ class SemiMarkovModule(nn.Module):
             em, rowterm, offset = hsmm.emission_scores(features, s['means'], s['cov_diag'], constraints, s['lengths_i32'])
         scores = HsmmScores(em, rowterm, offset, s['init'].detach(), s['trans'].detach(), s['lenp'].detach(), s['end'],
                             s['lengths_i32'], s['order'], s['C'], s['sparse'])
+        scores.decode_ids = s['decode_ids']
         log_det = torch.zeros(features.size(0), device=features.device, requires_grad=False)
         if return_elp:
             return scores, log_det, scores.elp
@@ -375,7 +381,7 @@ class SemiMarkovModule(nn.Module):
         dev = features.device
         spans = spans.to(dev)
         lut = torch.full((self.n_classes + 1,), -1, dtype=torch.long, device=dev)
-        vc = torch.arange(self.n_classes, device=dev) if valid_classes is None else s['valid_classes']
+        vc = torch.arange(self.n_classes, device=dev) if s['valid_classes'] is None else s['valid_classes']
         lut[vc] = torch.arange(len(vc), device=dev)
         local = torch.where(spans >= 0, lut[spans.clamp(min=0)], torch.full_like(spans, -1)).to(torch.int32).contiguous()
         score = hsmm.HsmmGoldScore.apply(*args, local)
@@ -398,13 +404,8 @@ class SemiMarkovModule(nn.Module):
             scores, _ = self.score_features(features, lengths, valid_classes, add_eos=add_eos, use_mean_z=use_mean_z,
                                             additional_allowed_ends_per_instance=additional_allowed_ends_per_instance,
                                             constraints=constraints)
-            dev = features.device
-            if valid_classes is None:
-                ids = torch.arange(self.n_classes + 1, device=dev, dtype=torch.int32)
-            else:
-                ids = torch.cat([valid_classes.to(dev), torch.tensor([self.n_classes], device=dev)]).to(torch.int32)
             spans, labels, _ = hsmm.viterbi_decode(scores.em, C, scores.init, scores.trans, scores.lenp, scores.end,
-                                                   scores.offset, scores.lengths_i32, scores.order, ids.contiguous(),
+                                                   scores.offset, scores.lengths_i32, scores.order, scores.decode_ids,
                                                    want_labels=return_labels, want_score=False,
                                                    trans_pred=None if scores.sparse is None else scores.sparse[0])
         def to_host(t):
