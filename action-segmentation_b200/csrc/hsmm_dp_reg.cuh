@@ -210,24 +210,28 @@ __global__ void __launch_bounds__(MAXT) dp_forward_kernel(const DpParams p) {
         nu = 0.0;
         const bool use_smem = (TM != 2) || dense_pass || W > 1;
 
-        float enext[F];
-#pragma unroll
-        for (int f = 0; f < F; ++f) enext[f] = (valid && f < T) ? __ldg(em_b + (size_t)f * ldc + c) : 0.0f;
+        // emission prefetch ring (4 frames ahead) and running output pointers: no per-frame 64-bit index math
+        const float* ep = em_b + c;
+        float e0 = (valid && 0 < T) ? __ldg(ep) : 0.0f;
+        float e1 = (valid && 1 < T) ? __ldg(ep + ldc) : 0.0f;
+        float e2 = (valid && 2 < T) ? __ldg(ep + 2 * ldc) : 0.0f;
+        float e3 = (valid && 3 < T) ? __ldg(ep + 3 * ldc) : 0.0f;
+        ep += 4 * ldc;
+        ST* gout = fgamma + (row0 + 1) * ldc + c;      // gamma[n]
+        ST* bout = fbeta + (row0 + 1) * ldc + c;       // beta[n]
+        uint32_t* pout = p.bp + (row0 + 1) * ldc + c;  // back-pointers of frame n
+        float* dout = p.fdelta + row0 + 1;
 
-        for (int n0 = 1; n0 <= T; n0 += F) {
-            float ecur[F];
-#pragma unroll
-            for (int f = 0; f < F; ++f) ecur[f] = enext[f];
-#pragma unroll
-            for (int f = 0; f < F; ++f) {
-                const int t = n0 - 1 + F + f;
-                enext[f] = (valid && t < T) ? __ldg(em_b + (size_t)t * ldc + c) : 0.0f;
-            }
-#pragma unroll
-            for (int f = 0; f < F; ++f) {
-                const int n = n0 + f;
-                if (n > T) break;
-                const ST e = (ST)ecur[f] * (ST)SC;
+#pragma unroll 1
+        for (int n = 1; n <= T; ++n) {
+            {
+                const float efr = e0;
+                e0 = e1;
+                e1 = e2;
+                e2 = e3;
+                e3 = (valid && n + 3 < T) ? __ldg(ep) : 0.0f;
+                ep += ldc;
+                const ST e = (ST)efr * (ST)SC;
                 nu += (double)gmprev;
                 ST gamma;
                 int bk = 0;
@@ -314,12 +318,14 @@ __global__ void __launch_bounds__(MAXT) dp_forward_kernel(const DpParams p) {
                     gm = NEG;
                     for (int q = 0; q < W; ++q) gm = fmaxf(gm, wmax_s[(n & 1) * W + q]);
                 }
-                if (!VIT && owner) fgamma[(row0 + n) * ldc + c] = gamma;
+                if (!VIT && owner) *gout = gamma;
+                gout += ldc;
                 if (n == T) {
-                    if (VIT && owner) p.bp[(row0 + n) * ldc + c] = (uint32_t)bk << 16;
+                    if (VIT && owner) *pout = (uint32_t)bk << 16;
                     break;
                 }
-                if (!VIT && gtid == 0) p.fdelta[row0 + n] = gm;
+                if (!VIT && gtid == 0) *dout = gm;
+                ++dout;
                 gmprev = gm;
                 // ---- phase 2: beta^[n][c2] = (+)_c1 gamma~[n][c1] + trans[c2,c1] - gm ---------------
                 if constexpr (VIT) {
@@ -369,7 +375,8 @@ __global__ void __launch_bounds__(MAXT) dp_forward_kernel(const DpParams p) {
                         slice_argmax<S>(best, bc);
                     }
                     beta = valid ? best - gm : NEG;
-                    if (owner) p.bp[(row0 + n) * ldc + c] = ((uint32_t)bk << 16) | (uint32_t)bc;
+                    if (owner) *pout = ((uint32_t)bk << 16) | (uint32_t)bc;
+                    pout += ldc;
                 } else {
                     if (TM == 2 && !dense_pass) {
                         if constexpr (TM == 2) {
@@ -417,7 +424,8 @@ __global__ void __launch_bounds__(MAXT) dp_forward_kernel(const DpParams p) {
                         }
                         beta = valid ? ((ST)trmax + mfix) + (ST)lg2(s) : (ST)NEG;
                     }
-                    if (owner) fbeta[(row0 + n) * ldc + c] = beta;
+                    if (owner) *bout = beta;
+                    bout += ldc;
                 }
             }
         }

@@ -21,8 +21,12 @@ import sys
 import threading
 import time
 
-import numpy as np
-import torch
+# the step keeps ~36 independent kernel chains in flight (one or two streams per task): give the driver enough hardware
+# work queues, or streams share a queue and serialise (the default of 8 caps the step at 8 concurrent kernels)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
@@ -47,6 +51,7 @@ def parse():
     ap.add_argument("--tmax", type=int, default=3000)
     ap.add_argument("--narration", action="store_true", help="configs[2]: add the -1e4 narration penalty tensor")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every step from Python instead of replaying a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-videos", type=int, default=5)
     ap.add_argument("--cpu-sample-frames", type=int, default=1500)
@@ -149,32 +154,34 @@ def packed_layout(tasks):
 # ---------------------------------------------------------------------------------------------
 # one step of the hot path, inputs resident in HBM, library kernels only
 # ---------------------------------------------------------------------------------------------
-def device_step(tasks, streams, packed, layout, world):
-    """One pass of the hot path over every task's batch, scheduled in three phases because the two streaming
-    kernels are persistent one-CTA-per-SM kernels that cannot share an SM with resident DP CTAs:
-      A  emission scoring of every task (tensor cores, back to back on one stream);
-      B  per task, on its own streams: forward -> backward and, concurrently, Viterbi (latency-bound DP
-         kernels: all tasks in flight together);
-      C  class-weighted feature sums of every task (d/d means) once the backward passes are done."""
+def device_step(tasks, streams, packed, layout, world, reduce=True, sched=None):
+    """One pass of the hot path over every task's batch.  Per task: emission scoring -> {forward -> backward ->
+    class-weighted feature sums} on the task's stream and, concurrently on a second stream, Viterbi (which
+    needs the emission scores only).  `sched` = "interleaved": every task's emission on its own stream;
+    "emfirst": all emissions back to back on one stream before any DP kernel (the emission kernel is a
+    persistent one-CTA-per-SM kernel and otherwise waits for whole SMs to drain)."""
     from action_segmentation_b200 import hsmm
     lib = hsmm._lib.load()
+    sched = sched or os.environ.get("HSMM_BENCH_SCHED", "interleaved")
     cur = torch.cuda.current_stream()
     packed.zero_()
     fork = torch.cuda.Event()
     fork.record(cur)
     n = len(tasks)
-    s_stream = streams[2 * n]
-    s_stream.wait_event(fork)
-    ems = []
-    with torch.cuda.stream(s_stream):
-        for tk in tasks:
-            ems.append(hsmm.emission_scores(tk.X, tk.means, tk.cov_diag, tk.penalty, tk.lengths_i32, params=tk.eparams))
-        em_done = torch.cuda.Event()
-        em_done.record(s_stream)
-    outs, views, dems, bwd_done = [], [], [], []
+    ems, em_evs = [], []
+    if sched == "emfirst":
+        s_stream = streams[2 * n]
+        s_stream.wait_event(fork)
+        with torch.cuda.stream(s_stream):
+            for tk in tasks:
+                ems.append(hsmm.emission_scores(tk.X, tk.means, tk.cov_diag, tk.penalty, tk.lengths_i32, params=tk.eparams))
+            ev = torch.cuda.Event()
+            ev.record(s_stream)
+        em_evs = [ev] * n
+    outs = []
     for i, tk in enumerate(tasks):
         st, st2 = streams[i], streams[n + i]
-        em, rowterm, offset = ems[i]
+        st.wait_event(fork)
         off, sizes = layout[i]
         v = []
         o = off
@@ -182,14 +189,22 @@ def device_step(tasks, streams, packed, layout, world):
             v.append(packed[o:o + m])
             o += m
         wx, d_trans, d_len, d_init, wsum, lz = v
-        views.append((wx, wsum, lz))
-        st2.wait_event(em_done)
+        if sched == "emfirst":
+            em, rowterm, offset = ems[i]
+            st.wait_event(em_evs[i])
+            em_ready = em_evs[i]
+        else:
+            with torch.cuda.stream(st):
+                em, rowterm, offset = hsmm.emission_scores(tk.X, tk.means, tk.cov_diag, tk.penalty, tk.lengths_i32,
+                                                           params=tk.eparams)
+                em_ready = torch.cuda.Event()
+                em_ready.record(st)
+        st2.wait_event(em_ready)
         with torch.cuda.stream(st2):
             spans, labels, score = hsmm.viterbi_decode(em, tk.C, tk.init, tk.trans, tk.lenp, tk.end, offset, tk.lengths_i32,
                                                        tk.order, tk.class_ids, want_labels=True, want_score=False,
                                                        trans_pred=tk.pred)
-            outs.append((spans, labels))
-        st.wait_event(em_done)
+            outs.append((spans, labels, em, offset))
         with torch.cuda.stream(st):
             xp = tk.penalty is not None
             logz, saved = hsmm.logz_forward(em, tk.C, tk.init, tk.trans, tk.lenp, tk.end, offset, tk.lengths_i32, tk.order,
@@ -198,29 +213,15 @@ def device_step(tasks, streams, packed, layout, world):
             _, _, _, d_em = hsmm.logz_backward(em, tk.C, tk.init, tk.trans, tk.lenp, tk.end, tk.lengths_i32, tk.order, g,
                                                saved, out=(d_init, d_trans.view(tk.C, tk.C), d_len.view(tk.K, tk.C)),
                                                trans_succ=tk.succ, f64_state=xp)
-            lz.copy_(logz.sum().float().reshape(1))
-            dems.append(d_em)
-            ev = torch.cuda.Event()
-            ev.record(st)
-            bwd_done.append(ev)
-    sched = os.environ.get("HSMM_BENCH_SCHED", "chain")
-    for i, (tk, d_em, (wx, wsum, lz)) in enumerate(zip(tasks, dems, views)):
-        if sched == "phases":  # every weighted sum after every backward pass, on one stream
-            if i == 0:
-                for ev in bwd_done:
-                    s_stream.wait_event(ev)
-            ws = s_stream
-        else:                  # each task's weighted sum right behind its backward pass
-            ws = streams[i]
-        with torch.cuda.stream(ws):
             hsmm._lib.check(lib.hsmm_weighted_feature_sums(hsmm._p(tk.X), hsmm._p(d_em), d_em.shape[2], hsmm._p(tk.lengths_i32),
                                                            tk.V, tk.Tmax, tk.D, tk.C, hsmm._p(wx), hsmm._p(wsum),
                                                            hsmm._stream()), "hsmm_weighted_feature_sums")
+            lz.copy_(logz.sum().float().reshape(1))
     for st in streams:
         ev = torch.cuda.Event()
         ev.record(st)
         cur.wait_event(ev)
-    if world > 1:
+    if world > 1 and reduce:
         torch.distributed.all_reduce(packed)
     return outs
 
@@ -438,8 +439,31 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident throughput -------------------------------------------------------------
+    # The step is ~90 library kernels on 36 streams: launched from Python it is host-bound, so after the eager
+    # warm-up it is captured ONCE into a CUDA graph (same kernels, same streams/dependencies, allocations from
+    # the graph's private pool) and the timed region replays it; the packed all-reduce follows each replay.
     for _ in range(args.warmup):
         device_step(tasks, streams, packed, layout, world)
+    barrier()
+    graph = None
+    launches_per_step = None
+    if not args.no_graph:
+        l_cap = _lib.launch_count()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            graph_outs = device_step(tasks, streams, packed, layout, world, reduce=False)  # noqa: F841 (kept alive)
+        launches_per_step = _lib.launch_count() - l_cap
+
+    def one_step():
+        if graph is None:
+            device_step(tasks, streams, packed, layout, world)
+        else:
+            graph.replay()
+            if world > 1:
+                torch.distributed.all_reduce(packed)
+
+    for _ in range(args.warmup):
+        one_step()
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -448,11 +472,11 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(args.steps):
-        device_step(tasks, streams, packed, layout, world)
+        one_step()
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
-    launches = _lib.launch_count() - l0
+    launches = (_lib.launch_count() - l0) if graph is None else launches_per_step * args.steps
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms, float(frames)], device=device, dtype=torch.float64)
     if world > 1:
@@ -534,6 +558,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": workload_name(args), "frames_per_step_per_gpu": frames, "videos_per_step_per_gpu":
                        sum(tk.V for tk in tasks), "parallelism": "dp%d over videos, 1 packed all-reduce/step" % world,
+                       "launch": "eager (Python)" if graph is None else "CUDA-graph replay of the step (captured after eager warm-up)",
                        "l2_policy": "inputs larger than L2 (%.1f GB of features per step per GPU)" % (frames * D * 4 / 1e9),
                        "dp_variants": sorted(set(_lib.dp_variant(tk.C, tk.K, 1, True) for tk in tasks))},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,

@@ -10,7 +10,8 @@ from action_segmentation_b200 import hsmm  # noqa: E402
 
 
 def main():
-    sys.argv = [sys.argv[0]] + sys.argv[1:]
+    em_first = "--em-first" in sys.argv
+    sys.argv = [a for a in sys.argv if a != "--em-first"]
     args = bench.parse()
     torch.cuda.set_device(0)
     tasks = bench.make_workload(args, 0, "cuda:0")
@@ -30,14 +31,30 @@ def main():
     import time
     h0 = time.perf_counter()
     host = []
+    pre = []
+    if em_first:
+        sA = streams[2 * n]
+        sA.wait_event(t0)
+        with torch.cuda.stream(sA):
+            for tk in tasks:
+                a = ev(); a.record(sA)
+                r = hsmm.emission_scores(tk.X, tk.means, tk.cov_diag, tk.penalty, tk.lengths_i32, params=tk.eparams)
+                b = ev(); b.record(sA)
+                pre.append((a, r, b))
+            all_em = ev(); all_em.record(sA)
     for i, tk in enumerate(tasks):
         st, st2 = streams[i], streams[n + i]
         st.wait_event(t0)
         m = {}
-        with torch.cuda.stream(st):
-            m["em0"] = ev(); m["em0"].record(st)
-            em, rowterm, offset = hsmm.emission_scores(tk.X, tk.means, tk.cov_diag, tk.penalty, tk.lengths_i32, params=tk.eparams)
-            m["em1"] = ev(); m["em1"].record(st)
+        if em_first:
+            m["em0"], (em, rowterm, offset), m["em1"] = pre[i]
+            st.wait_event(all_em)
+            m["em1"] = all_em
+        else:
+            with torch.cuda.stream(st):
+                m["em0"] = ev(); m["em0"].record(st)
+                em, rowterm, offset = hsmm.emission_scores(tk.X, tk.means, tk.cov_diag, tk.penalty, tk.lengths_i32, params=tk.eparams)
+                m["em1"] = ev(); m["em1"].record(st)
         with torch.cuda.stream(st2):
             st2.wait_event(m["em1"])
             m["vit0"] = ev(); m["vit0"].record(st2)
@@ -45,6 +62,7 @@ def main():
                                 want_labels=True, want_score=False, trans_pred=tk.pred)
             m["vit1"] = ev(); m["vit1"].record(st2)
         with torch.cuda.stream(st):
+            m["fwd0"] = ev(); m["fwd0"].record(st)
             logz, saved = hsmm.logz_forward(em, tk.C, tk.init, tk.trans, tk.lenp, tk.end, offset, tk.lengths_i32, tk.order,
                                             trans_pred=tk.pred)
             m["fwd1"] = ev(); m["fwd1"].record(st)
@@ -56,11 +74,11 @@ def main():
         marks.append(m)
         host.append((time.perf_counter() - h0) * 1e3)
     torch.cuda.synchronize()
-    print("task  C  host_ms |  em: start-end | fwd end | bwd end | wfs end | vit: start-end")
+    print("task  C  host_ms |  em: start-end | fwd start-end | bwd end | wfs end | vit: start-end")
     for i, (tk, m) in enumerate(zip(tasks, marks)):
         t = {k: t0.elapsed_time(v) for k, v in m.items()}
-        print("%3d %3d %7.2f | %6.2f-%6.2f | %6.2f | %6.2f | %6.2f | %6.2f-%6.2f" % (
-            i, tk.C, host[i], t["em0"], t["em1"], t["fwd1"], t["bwd1"], t["wfs1"], t["vit0"], t["vit1"]))
+        print("%3d %3d %7.2f | %6.2f-%6.2f | %6.2f-%6.2f | %6.2f | %6.2f | %6.2f-%6.2f" % (
+            i, tk.C, host[i], t["em0"], t["em1"], t["fwd0"], t["fwd1"], t["bwd1"], t["wfs1"], t["vit0"], t["vit1"]))
 
 
 if __name__ == "__main__":
