@@ -201,28 +201,34 @@ int launch_emission(const float* X, const float* w, const float* bias, const flo
 // four frame phases are reduced through shared memory at the end and flushed with one atomic per entry.
 // ---------------------------------------------------------------------------------------------
 constexpr int W_TF = 64;       // frames per tile
-constexpr int W_PH = 4;        // frame phases (thread groups working on different frames of the tile)
 constexpr int W_DQ = 64;       // float4 columns per CTA (256 feature dims)
-constexpr int W_THREADS = W_PH * W_DQ;
+constexpr int W_THREADS = 256;
 constexpr int W_UNROLL = 8;
 
-template <int CP>
-__global__ void __launch_bounds__(W_THREADS)
+// CP classes per CTA, split over CH thread groups (CPT = CP / CH accumulator rows per thread: 48 registers at
+// CP = 24 instead of 96, so that two CTAs fit an SM); the remaining 4 / CH groups take different frames.
+template <int CP, int CH>
+__global__ void __launch_bounds__(W_THREADS, (CP / CH <= 16 ? 2 : 1))
 weighted_sums_kernel(const float* __restrict__ X, const float* __restrict__ wgt, int ldc,
                      const int32_t* __restrict__ lengths, int B, int Tmax, int D, int C, int tiles_per_video,
                      float* __restrict__ out_wx, float* __restrict__ out_wsum) {
+    constexpr int CPT = CP / CH;   // classes per thread
+    constexpr int PH = 4 / CH;     // frame phases
+    static_assert(CPT % 4 == 0 && PH >= 1, "class tile");
     __shared__ __align__(16) float Ws[W_TF][CP];
+    __shared__ __align__(16) float Red[4][W_DQ * 4];
     const int tid = threadIdx.x;
-    const int dq = tid & (W_DQ - 1), ph = tid / W_DQ;
+    const int dq = tid & (W_DQ - 1), grp = tid / W_DQ;
+    const int ph = grp % PH, ch = grp / PH;
     const int d0 = blockIdx.y * (W_DQ * 4) + dq * 4;  // first feature dim of this thread
     const int cb = blockIdx.z * CP;                   // first class of this CTA
     const int nc = min(CP, C - cb);
     const bool dok = d0 < D;                          // D % 4 == 0 on this path
     const int ntiles = B * tiles_per_video;
 
-    float acc[CP][4];
+    float acc[CPT][4];
 #pragma unroll
-    for (int c = 0; c < CP; ++c) acc[c][0] = acc[c][1] = acc[c][2] = acc[c][3] = 0.0f;
+    for (int c = 0; c < CPT; ++c) acc[c][0] = acc[c][1] = acc[c][2] = acc[c][3] = 0.0f;
     float wsum = 0.0f;  // thread c < nc (of the d-block 0 CTAs) accumulates the column sums
 
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -243,19 +249,19 @@ weighted_sums_kernel(const float* __restrict__ X, const float* __restrict__ wgt,
         if (dok) {
             const float* xp = X + ((size_t)b * Tmax + t0) * D + d0;
 #pragma unroll
-            for (int f0 = 0; f0 < W_TF / W_PH; f0 += W_UNROLL) {
+            for (int f0 = 0; f0 < W_TF / PH; f0 += W_UNROLL) {
                 float4 x[W_UNROLL];
 #pragma unroll
                 for (int u = 0; u < W_UNROLL; ++u) {
-                    const int f = (f0 + u) * W_PH + ph;
+                    const int f = (f0 + u) * PH + ph;
                     x[u] = (f < nf) ? __ldg(reinterpret_cast<const float4*>(xp + (size_t)f * D)) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
 #pragma unroll
                 for (int u = 0; u < W_UNROLL; ++u) {
-                    const int f = (f0 + u) * W_PH + ph;
+                    const int f = (f0 + u) * PH + ph;
 #pragma unroll
-                    for (int c4 = 0; c4 < CP / 4; ++c4) {
-                        const float4 w = *reinterpret_cast<const float4*>(&Ws[f][c4 * 4]);
+                    for (int c4 = 0; c4 < CPT / 4; ++c4) {
+                        const float4 w = *reinterpret_cast<const float4*>(&Ws[f][ch * CPT + c4 * 4]);
                         const float wv[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
@@ -269,18 +275,22 @@ weighted_sums_kernel(const float* __restrict__ X, const float* __restrict__ wgt,
             }
         }
     }
-    // reduce the frame phases through shared memory (one class at a time), then one atomic per entry
-    __shared__ __align__(16) float Red[W_PH][W_DQ * 4];
+    // reduce the frame phases through shared memory (one class row per group at a time), one atomic per entry
 #pragma unroll
-    for (int c = 0; c < CP; ++c) {
+    for (int c = 0; c < CPT; ++c) {
         __syncthreads();
-        *reinterpret_cast<float4*>(&Red[ph][dq * 4]) = make_float4(acc[c][0], acc[c][1], acc[c][2], acc[c][3]);
+        *reinterpret_cast<float4*>(&Red[grp][dq * 4]) = make_float4(acc[c][0], acc[c][1], acc[c][2], acc[c][3]);
         __syncthreads();
-        if (c < nc && tid < W_DQ * 4) {
-            const int d = blockIdx.y * (W_DQ * 4) + tid;
-            if (d < D) {
-                const float v = (Red[0][tid] + Red[1][tid]) + (Red[2][tid] + Red[3][tid]);
-                atomicAdd(out_wx + (size_t)(cb + c) * D + d, v);
+        // thread (dd, h) sums the PH phase rows of class half h
+        for (int i = tid; i < CH * W_DQ * 4; i += W_THREADS) {
+            const int h = i / (W_DQ * 4), dd = i - h * (W_DQ * 4);
+            const int cls = h * CPT + c;
+            const int d = blockIdx.y * (W_DQ * 4) + dd;
+            if (cls < nc && d < D) {
+                float v = 0.0f;
+#pragma unroll
+                for (int q = 0; q < PH; ++q) v += Red[h * PH + q][dd];
+                atomicAdd(out_wx + (size_t)(cb + cls) * D + d, v);
             }
         }
     }
@@ -351,15 +361,15 @@ int launch_weighted_sums(const float* X, const float* wgt, int ldc, const int32_
     const int dblocks = (D + W_DQ * 4 - 1) / (W_DQ * 4);
     const int cp = C <= 8 ? 8 : (C <= 16 ? 16 : (C <= 24 ? 24 : 32));
     const int cblocks = (C + cp - 1) / cp;
-    int gx = (num_sms * (cp <= 16 ? 2 : 1)) / (dblocks * cblocks);  // resident CTAs: 203-246 registers at CP >= 24
+    int gx = (num_sms * 2) / (dblocks * cblocks);  // two resident CTAs per SM
     if (gx < 1) gx = 1;
     if (gx > B * tiles_per_video) gx = B * tiles_per_video;
     dim3 grid(gx, dblocks, cblocks);
     switch (cp) {
-        case 8: weighted_sums_kernel<8><<<grid, W_THREADS, 0, st>>>(X, wgt, ldc, lengths, B, Tmax, D, C, tiles_per_video, out_wx, out_wsum); break;
-        case 16: weighted_sums_kernel<16><<<grid, W_THREADS, 0, st>>>(X, wgt, ldc, lengths, B, Tmax, D, C, tiles_per_video, out_wx, out_wsum); break;
-        case 24: weighted_sums_kernel<24><<<grid, W_THREADS, 0, st>>>(X, wgt, ldc, lengths, B, Tmax, D, C, tiles_per_video, out_wx, out_wsum); break;
-        default: weighted_sums_kernel<32><<<grid, W_THREADS, 0, st>>>(X, wgt, ldc, lengths, B, Tmax, D, C, tiles_per_video, out_wx, out_wsum); break;
+        case 8: weighted_sums_kernel<8, 1><<<grid, W_THREADS, 0, st>>>(X, wgt, ldc, lengths, B, Tmax, D, C, tiles_per_video, out_wx, out_wsum); break;
+        case 16: weighted_sums_kernel<16, 1><<<grid, W_THREADS, 0, st>>>(X, wgt, ldc, lengths, B, Tmax, D, C, tiles_per_video, out_wx, out_wsum); break;
+        case 24: weighted_sums_kernel<24, 2><<<grid, W_THREADS, 0, st>>>(X, wgt, ldc, lengths, B, Tmax, D, C, tiles_per_video, out_wx, out_wsum); break;
+        default: weighted_sums_kernel<32, 2><<<grid, W_THREADS, 0, st>>>(X, wgt, ldc, lengths, B, Tmax, D, C, tiles_per_video, out_wx, out_wsum); break;
     }
     return check_launch("weighted_sums_kernel");
 }
