@@ -40,6 +40,8 @@ static int num_sms() {
 
 // implemented in the kernel translation units
 bool dp_reg_supported(int C, int L, int mode, bool sparse, bool xp);
+bool dp_lin_used(int C, int L, int mode, bool sparse, bool xp);
+int dp_lin_set_enabled(int on);
 const char* dp_reg_name(int C, int L, int mode, bool sparse, bool xp);
 int dp_reg_launch(DpParams p, int mode, cudaStream_t st);
 int launch_emission(const float*, const float*, const float*, const float*, const float*, const float*, const int32_t*, int, int, int,
@@ -79,12 +81,13 @@ struct Saved {  // layout of the `saved` buffer of hsmm_logz_forward
     float* fdelta;
     double* logz2;
     float* fflag;
+    float* bflag;
 };
 static size_t plane_elems(int B, int Tmax, int C) { return (size_t)B * (Tmax + 1) * (size_t)((C + 3) / 4 * 4); }
 static size_t saved_bytes(int B, int Tmax, int C, bool xp) {
     const size_t st = xp ? sizeof(double) : sizeof(float);
     size_t n = 2 * plane_elems(B, Tmax, C) * st + (size_t)B * sizeof(double);  // fbeta, fgamma, logz2
-    n += ((size_t)B * (Tmax + 1) + (size_t)B) * sizeof(float);                  // fdelta, fflag
+    n += ((size_t)B * (Tmax + 1) + 2 * (size_t)B) * sizeof(float);              // fdelta, fflag, bflag
     return n + 16;
 }
 static Saved carve(void* saved, int B, int Tmax, int C, bool xp) {
@@ -98,6 +101,7 @@ static Saved carve(void* saved, int B, int Tmax, int C, bool xp) {
     s.fgamma = base + n * st;
     s.fdelta = reinterpret_cast<float*>(base + 2 * n * st);
     s.fflag = s.fdelta + (size_t)B * (Tmax + 1);
+    s.bflag = s.fflag + B;
     return s;
 }
 
@@ -114,9 +118,17 @@ uint64_t hsmm_launch_count(void) { return g_launches.load(); }
 const char* hsmm_dp_variant(int C, int K, int mode, int flags) {
     const int L = K - 1;
     const bool sparse = (flags & 1) != 0, xp = (flags & 2) != 0 && mode != 0;
-    if (dp_reg_supported(C, L, mode, sparse, xp)) return dp_reg_name(C, L, mode, sparse, xp);
+    if (dp_reg_supported(C, L, mode, sparse, xp)) {
+        const char* nm = dp_reg_name(C, L, mode, sparse, xp);
+        if (!dp_lin_used(C, L, mode, sparse, xp)) return nm;
+        static thread_local char buf[160];
+        snprintf(buf, sizeof(buf), "lin+%s", nm);
+        return buf;
+    }
     return "unsupported";
 }
+
+int hsmm_set_linear_window(int enabled) { return dp_lin_set_enabled(enabled); }
 
 size_t hsmm_viterbi_workspace_bytes(int B, int Tmax, int C, int K) {
     (void)K;
@@ -197,7 +209,8 @@ int hsmm_logz_forward(const float* em, int ldc, const float* init, const float* 
     p.lengths = lengths; p.order = order; p.B = B; p.Tmax = Tmax; p.C = C; p.L = K - 1; p.ldc = ldc;
     p.xp = (flags & HSMM_FLAG_F64_STATE) ? 1 : 0;
     Saved s = carve(saved, B, Tmax, C, p.xp != 0);
-    p.fbeta = s.fbeta; p.fgamma = s.fgamma; p.fdelta = s.fdelta; p.logz2 = s.logz2; p.fflag = s.fflag; p.logz = out_logz;
+    p.fbeta = s.fbeta; p.fgamma = s.fgamma; p.fdelta = s.fdelta; p.logz2 = s.logz2; p.fflag = s.fflag; p.bflag = s.bflag;
+    p.logz = out_logz;
     p.trans_pred = trans_pred;
     if (!dp_reg_supported(C, p.L, 1, trans_pred != nullptr, p.xp != 0)) {
         set_error("hsmm_logz_forward: shape C=%d K=%d not supported (register-resident DP only)", C, K);
@@ -221,7 +234,7 @@ int hsmm_logz_backward(const float* em, int ldc, const float* init, const float*
     p.lengths = lengths; p.order = order; p.B = B; p.Tmax = Tmax; p.C = C; p.L = K - 1; p.ldc = ldc;
     p.xp = (flags & HSMM_FLAG_F64_STATE) ? 1 : 0;
     Saved s = carve(const_cast<void*>(saved), B, Tmax, C, p.xp != 0);
-    p.fbeta = s.fbeta; p.fgamma = s.fgamma; p.fdelta = s.fdelta; p.logz2 = s.logz2; p.fflag = s.fflag;
+    p.fbeta = s.fbeta; p.fgamma = s.fgamma; p.fdelta = s.fdelta; p.logz2 = s.logz2; p.fflag = s.fflag; p.bflag = s.bflag;
     p.trans_succ = trans_succ;
     p.grad = grad_logz; p.d_init = d_init; p.d_trans = d_trans; p.d_len = d_len; p.d_em = d_em;
     if (!dp_reg_supported(C, p.L, 2, trans_succ != nullptr, p.xp != 0)) {

@@ -111,7 +111,11 @@ struct DpParams {
     void* fgamma;   // (B, Tmax+1, ldc)  gamma[n], n = 1..T    (log2 domain; float, double when xp)
     float* fdelta;  // (B, Tmax+1)  per-frame normaliser increments delta_n, n = 1..T
     double* logz2;  // (B) log2 Z relative to the accumulated normaliser nu_T
-    float* fflag;   // (B) 1 when the video was recomputed against the dense matrix (sparse hint degenerate)
+    float* fflag;   // (B) bit 0: recomputed against the dense matrix (sparse hint degenerate); 2: the linear-window
+                    //     forward kernel could not certify the video -> the log-domain kernel recomputes it and
+                    //     sets bit 2 (value 4 or 5)
+    float* bflag;   // (B) 1: the linear-window backward kernel left the video to the log-domain kernel
+    int only_flagged;  // log-domain kernels: process only the videos flagged by the linear-window kernels
     double* logz;   // (B)
     // backward
     const float* grad;  // (B)

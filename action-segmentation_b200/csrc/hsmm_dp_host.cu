@@ -1,4 +1,6 @@
 // Host-side dispatch of the register-resident DP: shape support, variant names, launcher selection.
+#include <stdlib.h>
+
 #include "hsmm_dp_reg.cuh"
 
 namespace hsmm {
@@ -8,6 +10,29 @@ int dp_launch_fwd(DpParams p, cudaStream_t st);
 int dp_launch_fwd_xp(DpParams p, cudaStream_t st);
 int dp_launch_bwd(DpParams p, cudaStream_t st);
 int dp_launch_bwd_xp(DpParams p, cudaStream_t st);
+bool dp_lin_eligible(int C, int L, int mode, bool sparse, bool xp);
+int dp_lin_launch_fwd(DpParams p, cudaStream_t st);
+int dp_lin_launch_bwd(DpParams p, cudaStream_t st);
+
+// HSMM_DISABLE_LIN=1 keeps every video on the log-domain kernels (A/B comparisons, debugging)
+static std::atomic<int> g_lin{-1};
+static bool lin_enabled() {
+    int v = g_lin.load(std::memory_order_relaxed);
+    if (v < 0) {
+        const char* e = getenv("HSMM_DISABLE_LIN");
+        v = (e && e[0] == '1') ? 0 : 1;
+        g_lin.store(v, std::memory_order_relaxed);
+    }
+    return v == 1;
+}
+int dp_lin_set_enabled(int on) {
+    const int prev = lin_enabled() ? 1 : 0;
+    g_lin.store(on ? 1 : 0, std::memory_order_relaxed);
+    return prev;
+}
+bool dp_lin_used(int C, int L, int mode, bool sparse, bool xp) {
+    return mode != 0 && lin_enabled() && dp_lin_eligible(C, L, mode, sparse, xp);
+}
 
 bool dp_reg_supported(int C, int L, int mode, bool sparse, bool xp) { return choose(C, L, mode, sparse, xp).v >= 0; }
 
@@ -23,6 +48,14 @@ const char* dp_reg_name(int C, int L, int mode, bool sparse, bool xp) {
 
 int dp_reg_launch(DpParams p, int mode, cudaStream_t st) {
     if (mode == 0) return dp_launch_vit(p, st);
+    p.only_flagged = 0;
+    const bool sparse = (mode == 2) ? (p.trans_succ != nullptr) : (p.trans_pred != nullptr);
+    if (dp_lin_used(p.C, p.L, mode, sparse, p.xp != 0)) {
+        // linear-window kernel first; the log-domain kernel behind it recomputes the videos it flagged
+        const int rc = (mode == 1) ? dp_lin_launch_fwd(p, st) : dp_lin_launch_bwd(p, st);
+        if (rc) return rc;
+        p.only_flagged = 1;
+    }
     if (mode == 1) return p.xp ? dp_launch_fwd_xp(p, st) : dp_launch_fwd(p, st);
     return p.xp ? dp_launch_bwd_xp(p, st) : dp_launch_bwd(p, st);
 }

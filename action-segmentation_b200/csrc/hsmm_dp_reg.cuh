@@ -131,6 +131,9 @@ __global__ void __launch_bounds__(MAXT) dp_forward_kernel(const DpParams p) {
     const int b = p.order ? p.order[vidx] : vidx;
     const int T = p.lengths[b];
     const int bar_id = 1 + slot;
+    if constexpr (!VIT) {
+        if (p.only_flagged && p.fflag[b] != 2.0f) return;  // certified by the linear-window kernel (hsmm_dp_lin.cuh)
+    }
 
     // ---- per-lane constants ----------------------------------------------------------------
     float ln[LREG ? KR : 1];
@@ -479,7 +482,7 @@ __global__ void __launch_bounds__(MAXT) dp_forward_kernel(const DpParams p) {
     if constexpr (!VIT) {
         if (gtid == 0) {
             p.logz2[b] = (double)final_v;
-            p.fflag[b] = (TM == 2 && dense_pass) ? 1.0f : 0.0f;
+            p.fflag[b] = ((TM == 2 && dense_pass) ? 1.0f : 0.0f) + (p.only_flagged ? 4.0f : 0.0f);  // bit 2: recomputed here
             p.logz[b] = (nu + (double)final_v) * LN2 + (p.offset ? p.offset[b] : 0.0);
         }
     } else {
@@ -575,7 +578,8 @@ __global__ void __launch_bounds__(MAXT) dp_backward_kernel(const DpParams p) {
     const int b = p.order ? p.order[vidx] : vidx;
     const int T = p.lengths[b];
     const int bar_id = 1 + slot;
-    const bool dense_pass = (TM != 2) || (p.fflag[b] != 0.0f);
+    if (p.only_flagged && p.bflag[b] == 0.0f) return;  // done by the linear-window kernel (hsmm_dp_lin.cuh)
+    const bool dense_pass = (TM != 2) || (((int)p.fflag[b]) & 1);
     const bool use_smem = (TM != 2) || dense_pass || W > 1;
 
     float Bq[KR], El[KR];

@@ -184,6 +184,13 @@ const char* hsmm_dp_variant(int C, int K, int mode /*0 viterbi, 1 forward, 2 bac
                             int flags /* bit 0: sparse transition lists, bit 1: f64 state */);
 uint64_t hsmm_launch_count(void);
 
+/* hsmm_logz_forward / hsmm_logz_backward run a linear-window (block floating point) kernel on the shapes that
+ * fit one warp per video and recompute the videos it cannot certify with the log-domain kernel; results do not
+ * depend on the switch.  hsmm_set_linear_window(0) keeps every video on the log-domain kernels (A/B runs);
+ * returns the previous setting.  Environment: HSMM_DISABLE_LIN=1.  hsmm_dp_variant reports "lin+" in front
+ * of the variant name when the linear-window kernel is used for that shape. */
+int hsmm_set_linear_window(int enabled);
+
 #ifdef __cplusplus
 }
 #endif

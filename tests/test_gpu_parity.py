@@ -375,3 +375,137 @@ def test_full_size_properties():
         sc = O.path_score(segs, em_h[b, :T, :C], s["init"].detach().cpu().numpy().astype(np.float64),
                           s["trans"].detach().cpu().numpy().astype(np.float64), s["lenp"].detach().cpu().numpy().astype(np.float64))
         assert abs(sc + off_h[b] - float(score[b])) < 1e-6 * abs(float(score[b]))
+
+
+# ---------------------------------------------------------------------------------------------
+# linear-window (block floating point) kernels vs the log-domain kernels
+# ---------------------------------------------------------------------------------------------
+def _saved_flags(saved, B, Tmax, C):
+    """(fflag, bflag) of the `saved` buffer of hsmm_logz_forward (layout: hsmm_api.cu `carve`)."""
+    import action_segmentation_b200 as pkg
+    plane = B * (Tmax + 1) * pkg.hsmm.ldc_of(C)
+    off = B * 8 + 2 * plane * 4 + B * (Tmax + 1) * 4
+    f = saved[off:off + 8 * B].view(torch.float32).cpu().numpy()
+    return f[:B], f[B:]
+
+
+def _fwd_bwd(prob, d, sp, w):
+    import action_segmentation_b200 as pkg
+    C = prob["em"].shape[2]
+    logz, saved = pkg.hsmm.logz_forward(d["em"], C, d["init"], d["trans"], d["lenp"], d["end"], None, d["lengths_i32"],
+                                        d["order"], trans_pred=sp[0])
+    fflag = _saved_flags(saved, prob["em"].shape[0], prob["em"].shape[1], C)[0].copy()
+    g = torch.from_numpy(w).float().cuda()
+    grads = pkg.hsmm.logz_backward(d["em"], C, d["init"], d["trans"], d["lenp"], d["end"], d["lengths_i32"], d["order"], g,
+                                   saved, trans_succ=sp[1])
+    torch.cuda.synchronize()
+    bflag = _saved_flags(saved, prob["em"].shape[0], prob["em"].shape[1], C)[1].copy()
+    return logz, grads, fflag, bflag
+
+
+LIN_SHAPES = [
+    # (B, Tmax, C, K, chain, ends, em scale)
+    (9, 300, 23, 20, True, True, 3.0),    # lin<20,1> sparse (flagship)
+    (9, 300, 13, 20, True, True, 12.0),   # lin<10,2> sparse, peaked emissions
+    (7, 200, 23, 20, False, False, 3.0),  # lin<20,1> dense transitions in registers
+    (7, 200, 16, 20, False, False, 25.0),  # lin<10,2> dense
+    (6, 150, 5, 52, False, False, 3.0),   # lin<13,4>
+    (6, 150, 16, 50, False, False, 3.0),  # lin<25,2>
+    (6, 120, 3, 30, False, False, 3.0),   # lin<32,1>
+]
+
+
+@pytest.mark.parametrize("shape", LIN_SHAPES, ids=lambda s: "B%d_T%d_C%d_K%d_s%g" % (s[0], s[1], s[2], s[3], s[6]))
+def test_linear_window_matches_log_domain_and_oracle(shape):
+    """Same inputs through the linear-window kernels and (hsmm_set_linear_window(0)) the log-domain kernels: logZ,
+    every expected count and the frame posteriors agree to fp32 rounding, and both agree with the fp64 oracle."""
+    import action_segmentation_b200 as pkg
+    B, Tmax, C, K, chain, ends, scale = shape
+    rng = np.random.default_rng(300 + C * 7 + K)
+    prob = random_problem(rng, B, Tmax, C, K, Tmin=Tmax // 3, chain=chain, ends=ends, scale=scale)
+    # realistic duration rates (the reference initialises Poisson rate 1 and fits mean segment lengths)
+    prob["lenp"] = O.poisson_length_log_probs(np.log(rng.uniform(1.0, 12.0, size=C)), K)
+    prob["lenp"] = O.clamp_len_table(prob["lenp"], Tmax)
+    d = to_dev(prob)
+    sp = sparse_lists(prob) if chain else (None, None)
+    w = rng.uniform(0.5, 1.5, size=B)
+    assert pkg._lib.dp_variant(C, K, 1, chain).startswith("lin+")
+    try:
+        lz1, g1, ff1, bf1 = _fwd_bwd(prob, d, sp, w)
+        pkg._lib.set_linear_window(False)
+        assert not pkg._lib.dp_variant(C, K, 1, chain).startswith("lin+")
+        lz0, g0, ff0, bf0 = _fwd_bwd(prob, d, sp, w)
+    finally:
+        pkg._lib.set_linear_window(True)
+    assert (ff0 < 2).all() and (bf0 == 0).all()
+    if K <= 32:
+        # ordinary inputs with short windows are certified by the linear-window kernels: nothing goes to the fallback
+        assert (ff1 < 2).all() and (bf1 == 0).all(), (ff1, bf1)
+    else:
+        # Poisson tails below 2^-100 inside a long window: the length-table check (reason bit 8) hands every video over
+        assert (ff1 >= 4).all() and (bf1 == 9).all(), (ff1, bf1)
+    assert torch.allclose(lz1, lz0, rtol=2e-6, atol=5e-4)
+    for a, b_ in zip(g1, g0):  # two fp32 computations, each within 1e-4 of the oracle (checked below)
+        assert rel_err(a.cpu().numpy(), b_.cpu().numpy()) < 2.5e-4
+    f32 = lambda x: x.astype(np.float32).astype(np.float64)  # noqa: E731
+    ref_logz, acc = O.batch_logz_and_counts(f32(prob["em"]), prob["lengths"], f32(prob["init"]), f32(prob["trans"]),
+                                            f32(prob["lenp"]), prob["end"], w)
+    assert np.allclose(lz1.cpu().numpy(), ref_logz, rtol=1e-5, atol=1e-4)
+    mine = dict(E_init=g1[0], E_trans=g1[1], E_len=g1[2], E_em=g1[3][:, :, :C])
+    for k, v in mine.items():
+        assert rel_err(v.cpu().numpy(), acc[k]) < 1e-4, (k, rel_err(v.cpu().numpy(), acc[k]))
+
+
+@pytest.mark.parametrize("case", ["tiny_rates", "no_self_loops", "no_path", "collapse"])
+def test_linear_window_flags_fall_back_to_log_domain(case):
+    """Inputs the float window cannot certify: the videos are flagged, recomputed by the log-domain kernels, and the
+    results still match the oracle."""
+    import action_segmentation_b200 as pkg
+    rng = np.random.default_rng(17)
+    B, Tmax, C, K = 6, 60, 9, 20
+    prob = random_problem(rng, B, Tmax, C, K, Tmin=30, chain=True, ends=True, scale=3.0)
+    expect_all = False
+    if case == "tiny_rates":      # usable lengths with probability below 2^-100: the window could overflow
+        prob["lenp"] = O.poisson_length_log_probs(np.log(np.full(C, 0.02)), K)
+        expect_all = True
+    elif case == "no_self_loops":  # strict chain c -> c+1 only and peaked emissions: a class sum collapses when its
+        logits = np.full((C, C), O.BIG_NEG)  # only mass leaves the window
+        for c in range(C - 1):
+            logits[c + 1, c] = 0.0
+        logits[C - 1, C - 1] = 0.0
+        prob["trans"] = O.log_softmax(logits, axis=0)
+        prob["em"] = prob["em"] * 10.0
+        prob["lengths"][:] = rng.integers(3 * C, Tmax + 1, size=B)
+    elif case == "no_path":      # chain longer than the video: every path pays -1e9
+        prob["lengths"][1] = 4
+        prob["lengths"][3] = 6
+        end = np.full((B, C), O.BIG_NEG)
+        end[:, C - 1] = 0.0
+        prob["end"] = end
+    elif case == "collapse":     # entry mass into a class decays by 2^-40 per frame, then everything older expires
+        prob = random_problem(rng, B, Tmax, 5, K, Tmin=50, chain=False, ends=False, scale=1.0)
+        C = 5
+        prob["em"][:, :, 1] = -np.arange(Tmax)[None, :] * 28.0 * (np.arange(Tmax)[None, :] < 12)
+        prob["trans"][1, :] = -40.0   # hard to enter class 1 ...
+        prob["init"] = np.log(np.array([0.01, 0.96, 0.01, 0.01, 0.01]))  # ... except at the start
+    prob["lenp"] = O.clamp_len_table(prob["lenp"], Tmax)
+    d = to_dev(prob)
+    chain = case != "collapse"
+    sp = sparse_lists(prob) if chain else (None, None)
+    w = np.ones(B)
+    assert pkg._lib.dp_variant(C, K, 1, chain).startswith("lin+")
+    lz, g, ff, bf = _fwd_bwd(prob, d, sp, w)
+    n_flagged = int((ff >= 4).sum())
+    if expect_all:
+        assert n_flagged == B and (bf >= 1).all()
+    if case == "no_path":
+        assert ff[1] >= 4 and ff[3] >= 4
+    f32 = lambda x: x.astype(np.float32).astype(np.float64)  # noqa: E731
+    ref_logz, acc = O.batch_logz_and_counts(f32(prob["em"]), prob["lengths"], f32(prob["init"]), f32(prob["trans"]),
+                                            f32(prob["lenp"]), prob["end"], w)
+    assert np.allclose(lz.cpu().numpy(), ref_logz, rtol=1e-5, atol=1e-4), (case, n_flagged)
+    if case != "no_path":  # (the -1e9-penalised videos resolve their counts to fp32-at-1e9 noise only)
+        mine = dict(E_init=g[0], E_trans=g[1], E_len=g[2], E_em=g[3][:, :, :C])
+        for k, v in mine.items():
+            assert rel_err(v.cpu().numpy(), acc[k]) < 1e-4, (case, k, rel_err(v.cpu().numpy(), acc[k]), n_flagged)
+    print(case, "flagged forward:", n_flagged, "backward:", int((bf > 0).sum()))
