@@ -132,7 +132,8 @@ int hsmm_set_linear_window(int enabled) { return dp_lin_set_enabled(enabled); }
 
 size_t hsmm_viterbi_workspace_bytes(int B, int Tmax, int C, int K) {
     (void)K;
-    return plane_elems(B, Tmax, C) * sizeof(uint32_t);
+    // [beta / back-pointer plane][predecessor plane][normaliser increments (B, Tmax+1)][flags (B)]
+    return 2 * plane_elems(B, Tmax, C) * sizeof(uint32_t) + ((size_t)B * (Tmax + 1) + (size_t)B) * sizeof(float);
 }
 
 size_t hsmm_logz_saved_bytes(int B, int Tmax, int C, int K, int flags) {
@@ -184,6 +185,10 @@ int hsmm_viterbi(const float* em, int ldc, const float* init, const float* trans
     p.em = em; p.init = init; p.trans = trans; p.lenp = lenp; p.end = end; p.offset = offset;
     p.lengths = lengths; p.order = order; p.B = B; p.Tmax = Tmax; p.C = C; p.L = K - 1; p.ldc = ldc;
     p.bp = reinterpret_cast<uint32_t*>(workspace); p.class_ids = class_ids; p.spans = out_spans; p.labels = out_labels;
+    p.vbeta = reinterpret_cast<float*>(workspace);
+    p.vpred = reinterpret_cast<uint32_t*>(workspace) + plane_elems(B, Tmax, C);
+    p.vdelta = reinterpret_cast<float*>(p.vpred + plane_elems(B, Tmax, C));
+    p.vflag = p.vdelta + (size_t)B * (Tmax + 1);
     p.score = out_score; p.trans_pred = trans_pred;
     if (dp_reg_supported(C, p.L, 0, trans_pred != nullptr, false)) return dp_reg_launch(p, 0, (cudaStream_t)stream);
     set_error("hsmm_viterbi: shape C=%d K=%d exceeds on-chip capacity", C, K);

@@ -261,14 +261,13 @@ weighted_sums_kernel(const float* __restrict__ X, const float* __restrict__ wgt,
                     const int f = (f0 + u) * PH + ph;
 #pragma unroll
                     for (int c4 = 0; c4 < CPT / 4; ++c4) {
+                        // packed fp32 FMAs (FFMA2): one instruction updates the accumulators of two classes
                         const float4 w = *reinterpret_cast<const float4*>(&Ws[f][ch * CPT + c4 * 4]);
-                        const float wv[4] = {w.x, w.y, w.z, w.w};
+                        const float xs[4] = {x[u].x, x[u].y, x[u].z, x[u].w};
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            acc[c4 * 4 + q][0] = fmaf(wv[q], x[u].x, acc[c4 * 4 + q][0]);
-                            acc[c4 * 4 + q][1] = fmaf(wv[q], x[u].y, acc[c4 * 4 + q][1]);
-                            acc[c4 * 4 + q][2] = fmaf(wv[q], x[u].z, acc[c4 * 4 + q][2]);
-                            acc[c4 * 4 + q][3] = fmaf(wv[q], x[u].w, acc[c4 * 4 + q][3]);
+                        for (int d = 0; d < 4; ++d) {
+                            ffma2(acc[c4 * 4 + 0][d], acc[c4 * 4 + 1][d], w.x, w.y, xs[d], xs[d]);
+                            ffma2(acc[c4 * 4 + 2][d], acc[c4 * 4 + 3][d], w.z, w.w, xs[d], xs[d]);
                         }
                     }
                 }

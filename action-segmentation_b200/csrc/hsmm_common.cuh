@@ -72,6 +72,21 @@ __device__ __forceinline__ float warp_max(float v) {
     for (int off = 16; off > 0; off >>= 1) v = fmaxf(v, __shfl_xor_sync(FULL, v, off));
     return v;
 }
+// packed fp32 FMA (sm_100a FFMA2): (d0, d1) += (a0, a1) * (b0, b1), each lane rounded like fmaf
+__device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+    unsigned long long a, b, c;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(c) : "f"(d0), "f"(d1));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(c) : "l"(a), "l"(b));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(c));
+}
+// whole-warp maximum in one instruction (sm_100a: redux.sync.max.f32 -> CREDUX.MAX.F32)
+__device__ __forceinline__ float warp_max_redux(float v) {
+    float r;
+    asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+    return r;
+}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(FULL, v, off);
@@ -105,6 +120,11 @@ struct DpParams {
     int64_t* spans;           // (B, Tmax+1)
     int64_t* labels;          // (B, Tmax) or null
     double* score;            // (B) or null
+    // deferred-arg-max Viterbi (hsmm_dp_vit2.cuh); vbeta aliases bp
+    float* vbeta;     // (B, Tmax+1, ldc) beta^[n][c]
+    uint32_t* vpred;  // (B, Tmax+1, ldc) arg-max predecessor class of a segment start
+    float* vdelta;    // (B, Tmax+1) normaliser increments
+    float* vflag;     // (B) 1: no path through the sparse transition hint -> dp_forward_kernel<VIT> decodes the video
     // forward
     int xp;         // 1: per-class state (and fbeta/fgamma) in double -- see state_t in hsmm_dp_reg.cuh
     void* fbeta;    // (B, Tmax+1, ldc)  beta[n], n = 0..T-1   (log2 domain; float, double when xp)

@@ -13,6 +13,8 @@ int dp_launch_bwd_xp(DpParams p, cudaStream_t st);
 bool dp_lin_eligible(int C, int L, int mode, bool sparse, bool xp);
 int dp_lin_launch_fwd(DpParams p, cudaStream_t st);
 int dp_lin_launch_bwd(DpParams p, cudaStream_t st);
+bool dp_vit2_eligible(int C, int L, bool sparse);
+int dp_vit2_launch(DpParams p, cudaStream_t st);
 
 // HSMM_DISABLE_LIN=1 keeps every video on the log-domain kernels (A/B comparisons, debugging)
 static std::atomic<int> g_lin{-1};
@@ -31,7 +33,8 @@ int dp_lin_set_enabled(int on) {
     return prev;
 }
 bool dp_lin_used(int C, int L, int mode, bool sparse, bool xp) {
-    return mode != 0 && lin_enabled() && dp_lin_eligible(C, L, mode, sparse, xp);
+    if (!lin_enabled()) return false;
+    return mode == 0 ? dp_vit2_eligible(C, L, sparse) : dp_lin_eligible(C, L, mode, sparse, xp);
 }
 
 bool dp_reg_supported(int C, int L, int mode, bool sparse, bool xp) { return choose(C, L, mode, sparse, xp).v >= 0; }
@@ -47,8 +50,16 @@ const char* dp_reg_name(int C, int L, int mode, bool sparse, bool xp) {
 }
 
 int dp_reg_launch(DpParams p, int mode, cudaStream_t st) {
-    if (mode == 0) return dp_launch_vit(p, st);
     p.only_flagged = 0;
+    if (mode == 0) {
+        if (dp_lin_used(p.C, p.L, 0, p.trans_pred != nullptr, false)) {
+            // deferred-arg-max kernel; behind it the generic kernel decodes the videos whose sparse hint was degenerate
+            const int rc = dp_vit2_launch(p, st);
+            if (rc || p.trans_pred == nullptr) return rc;
+            p.only_flagged = 1;
+        }
+        return dp_launch_vit(p, st);
+    }
     const bool sparse = (mode == 2) ? (p.trans_succ != nullptr) : (p.trans_pred != nullptr);
     if (dp_lin_used(p.C, p.L, mode, sparse, p.xp != 0)) {
         // linear-window kernel first; the log-domain kernel behind it recomputes the videos it flagged

@@ -33,12 +33,6 @@ constexpr float LIN_DEAD = -1.0e8f;         // log2 units: below this a class ha
 constexpr float LIN_FLOOR = -121.0f;        // lg2 of (L <= 32 newly flushed elements, each < 2^-126)
 constexpr float LIN_RELEVANT = -24.0f;
 
-__device__ __forceinline__ float warp_max_redux(float v) {
-    float r;
-    asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
-    return r;
-}
-
 struct LinTracker {
     float ua, ub;
     int cnt;

@@ -93,6 +93,7 @@ __global__ void __launch_bounds__(MAXT) dp_forward_kernel(const DpParams p) {
     const int cpad = W * CPW;
     const int ldT = ld_trans(W, S);
     const float SC = VIT ? 1.0f : LOG2E;
+    constexpr int FG = (LREG && MAXT <= 512) ? F : 1;  // frames per prefetch group (register budget of the big variants)
 
     // shared layout: [transT C*ldT (TM==1)] [len columns KR*G (!LREG)] [per group: gamma 2*cpad (ST), warp maxima 2*W]
     float* transT = smem;
@@ -133,6 +134,8 @@ __global__ void __launch_bounds__(MAXT) dp_forward_kernel(const DpParams p) {
     const int bar_id = 1 + slot;
     if constexpr (!VIT) {
         if (p.only_flagged && p.fflag[b] != 2.0f) return;  // certified by the linear-window kernel (hsmm_dp_lin.cuh)
+    } else {
+        if (p.only_flagged && p.vflag[b] == 0.0f) return;  // decoded by the deferred-arg-max kernel (hsmm_dp_vit2.cuh)
     }
 
     // ---- per-lane constants ----------------------------------------------------------------
@@ -213,27 +216,32 @@ __global__ void __launch_bounds__(MAXT) dp_forward_kernel(const DpParams p) {
         nu = 0.0;
         const bool use_smem = (TM != 2) || dense_pass || W > 1;
 
-        // emission prefetch ring (4 frames ahead) and running output pointers: no per-frame 64-bit index math
+        // emission prefetch: the next group of FG frames is in flight while this group is processed (static register
+        // names -- a rotating ring makes every frame wait for the load issued one frame earlier); running output
+        // pointers: no per-frame 64-bit index math
         const float* ep = em_b + c;
-        float e0 = (valid && 0 < T) ? __ldg(ep) : 0.0f;
-        float e1 = (valid && 1 < T) ? __ldg(ep + ldc) : 0.0f;
-        float e2 = (valid && 2 < T) ? __ldg(ep + 2 * ldc) : 0.0f;
-        float e3 = (valid && 3 < T) ? __ldg(ep + 3 * ldc) : 0.0f;
-        ep += 4 * ldc;
+        float enext[FG];
+#pragma unroll
+        for (int f = 0; f < FG; ++f) enext[f] = (valid && f < T) ? __ldg(ep + f * ldc) : 0.0f;
+        ep += FG * ldc;
         ST* gout = fgamma + (row0 + 1) * ldc + c;      // gamma[n]
         ST* bout = fbeta + (row0 + 1) * ldc + c;       // beta[n]
         uint32_t* pout = p.bp + (row0 + 1) * ldc + c;  // back-pointers of frame n
         float* dout = p.fdelta + row0 + 1;
 
 #pragma unroll 1
-        for (int n = 1; n <= T; ++n) {
-            {
-                const float efr = e0;
-                e0 = e1;
-                e1 = e2;
-                e2 = e3;
-                e3 = (valid && n + 3 < T) ? __ldg(ep) : 0.0f;
-                ep += ldc;
+        for (int n0 = 1; n0 <= T; n0 += FG) {
+            float ecur[FG];
+#pragma unroll
+            for (int f = 0; f < FG; ++f) ecur[f] = enext[f];
+#pragma unroll
+            for (int f = 0; f < FG; ++f) enext[f] = (valid && n0 - 1 + FG + f < T) ? __ldg(ep + f * ldc) : 0.0f;
+            ep += FG * ldc;
+#pragma unroll
+            for (int f = 0; f < FG; ++f) {
+                const int n = n0 + f;
+                if (n > T) break;
+                const float efr = ecur[f];
                 const ST e = (ST)efr * (ST)SC;
                 nu += (double)gmprev;
                 ST gamma;
@@ -310,7 +318,7 @@ __global__ void __launch_bounds__(MAXT) dp_forward_kernel(const DpParams p) {
                 }
                 gprev = gamma;
                 // ---- group maximum of gamma: the normaliser increment ----------------------------
-                float gm = warp_max(owner ? (float)gamma : NEG);
+                float gm = warp_max_redux(owner ? (float)gamma : NEG);
                 ST* gs = gam_s + (n & 1) * cpad;
                 if (W > 1 && lane == 0) wmax_s[(n & 1) * W + wig] = gm;
                 if (use_smem) {

@@ -163,6 +163,7 @@ def device_step(tasks, streams, packed, layout, world, reduce=True, sched=None):
     from action_segmentation_b200 import hsmm
     lib = hsmm._lib.load()
     sched = sched or os.environ.get("HSMM_BENCH_SCHED", "interleaved")
+    skip = set(filter(None, os.environ.get("HSMM_BENCH_SKIP", "").split(",")))  # ablation only: invalid as a bench number
     cur = torch.cuda.current_stream()
     packed.zero_()
     fork = torch.cuda.Event()
@@ -195,16 +196,24 @@ def device_step(tasks, streams, packed, layout, world, reduce=True, sched=None):
             em_ready = em_evs[i]
         else:
             with torch.cuda.stream(st):
-                em, rowterm, offset = hsmm.emission_scores(tk.X, tk.means, tk.cov_diag, tk.penalty, tk.lengths_i32,
-                                                           params=tk.eparams)
+                if "em" in skip and getattr(tk, "em_cache", None) is not None:
+                    em, rowterm, offset = tk.em_cache
+                else:
+                    em, rowterm, offset = hsmm.emission_scores(tk.X, tk.means, tk.cov_diag, tk.penalty, tk.lengths_i32,
+                                                               params=tk.eparams)
+                    if "em" in skip:
+                        tk.em_cache = (em, rowterm, offset)
                 em_ready = torch.cuda.Event()
                 em_ready.record(st)
         st2.wait_event(em_ready)
         with torch.cuda.stream(st2):
-            spans, labels, score = hsmm.viterbi_decode(em, tk.C, tk.init, tk.trans, tk.lenp, tk.end, offset, tk.lengths_i32,
-                                                       tk.order, tk.class_ids, want_labels=True, want_score=False,
-                                                       trans_pred=tk.pred)
-            outs.append((spans, labels, em, offset))
+            if "vit" in skip:
+                outs.append((None, None, em, offset))
+            else:
+                spans, labels, score = hsmm.viterbi_decode(em, tk.C, tk.init, tk.trans, tk.lenp, tk.end, offset, tk.lengths_i32,
+                                                           tk.order, tk.class_ids, want_labels=True, want_score=False,
+                                                           trans_pred=tk.pred)
+                outs.append((spans, labels, em, offset))
         with torch.cuda.stream(st):
             xp = tk.penalty is not None
             logz, saved = hsmm.logz_forward(em, tk.C, tk.init, tk.trans, tk.lenp, tk.end, offset, tk.lengths_i32, tk.order,
@@ -213,9 +222,10 @@ def device_step(tasks, streams, packed, layout, world, reduce=True, sched=None):
             _, _, _, d_em = hsmm.logz_backward(em, tk.C, tk.init, tk.trans, tk.lenp, tk.end, tk.lengths_i32, tk.order, g,
                                                saved, out=(d_init, d_trans.view(tk.C, tk.C), d_len.view(tk.K, tk.C)),
                                                trans_succ=tk.succ, f64_state=xp)
-            hsmm._lib.check(lib.hsmm_weighted_feature_sums(hsmm._p(tk.X), hsmm._p(d_em), d_em.shape[2], hsmm._p(tk.lengths_i32),
-                                                           tk.V, tk.Tmax, tk.D, tk.C, hsmm._p(wx), hsmm._p(wsum),
-                                                           hsmm._stream()), "hsmm_weighted_feature_sums")
+            if "ws" not in skip:
+                hsmm._lib.check(lib.hsmm_weighted_feature_sums(hsmm._p(tk.X), hsmm._p(d_em), d_em.shape[2],
+                                                               hsmm._p(tk.lengths_i32), tk.V, tk.Tmax, tk.D, tk.C, hsmm._p(wx),
+                                                               hsmm._p(wsum), hsmm._stream()), "hsmm_weighted_feature_sums")
             lz.copy_(logz.sum().float().reshape(1))
     for st in streams:
         ev = torch.cuda.Event()
@@ -278,37 +288,43 @@ def build_models(tasks, args):
 # ---------------------------------------------------------------------------------------------
 # per-kernel durations (serialised on one stream, CUDA events) -> dominant kernel roofline
 # ---------------------------------------------------------------------------------------------
-def kernel_breakdown(tasks, reps=2):
+def kernel_breakdown(tasks, reps=3):
+    """Per-kernel device time of one step with every launch serialised on one stream (CUDA events around each
+    call; best of `reps` per launch, summed over the step's launches)."""
     from action_segmentation_b200 import hsmm
     names = ["emission", "logz_forward", "logz_backward", "weighted_feature_sums", "viterbi"]
-    acc = {n: 0.0 for n in names}
+    best = {}
     launches = {n: 0 for n in names}
 
-    def timed(name, fn):
+    def timed(key, fn):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         r = fn()
         b.record()
         b.synchronize()
-        acc[name] += a.elapsed_time(b)
-        launches[name] += 1
+        best[key] = min(best.get(key, 1e30), a.elapsed_time(b))
         return r
 
-    for _ in range(reps):
-        for tk in tasks:
-            em, rowterm, offset = timed("emission", lambda: hsmm.emission_scores(tk.X, tk.means, tk.cov_diag, tk.penalty, tk.lengths_i32,
-                                                                                    params=tk.eparams))
+    for rep in range(reps):
+        for i, tk in enumerate(tasks):
+            em, rowterm, offset = timed(("emission", i), lambda: hsmm.emission_scores(tk.X, tk.means, tk.cov_diag, tk.penalty,
+                                                                                         tk.lengths_i32, params=tk.eparams))
             xp = tk.penalty is not None
-            logz, saved = timed("logz_forward", lambda: hsmm.logz_forward(em, tk.C, tk.init, tk.trans, tk.lenp, tk.end, offset,
-                                                                          tk.lengths_i32, tk.order, trans_pred=tk.pred,
-                                                                          f64_state=xp))
+            logz, saved = timed(("logz_forward", i), lambda: hsmm.logz_forward(em, tk.C, tk.init, tk.trans, tk.lenp, tk.end, offset,
+                                                                               tk.lengths_i32, tk.order, trans_pred=tk.pred,
+                                                                               f64_state=xp))
             g = torch.full((tk.V,), 1.0 / tk.V, device=em.device)
-            d = timed("logz_backward", lambda: hsmm.logz_backward(em, tk.C, tk.init, tk.trans, tk.lenp, tk.end, tk.lengths_i32,
-                                                                  tk.order, g, saved, trans_succ=tk.succ, f64_state=xp))
-            timed("weighted_feature_sums", lambda: hsmm.weighted_feature_sums(tk.X, d[3], tk.C, tk.lengths_i32))
-            timed("viterbi", lambda: hsmm.viterbi_decode(em, tk.C, tk.init, tk.trans, tk.lenp, tk.end, offset, tk.lengths_i32,
-                                                         tk.order, tk.class_ids, want_score=False, trans_pred=tk.pred))
-    return {n: acc[n] / reps for n in names}, {n: launches[n] // reps for n in names}
+            d = timed(("logz_backward", i), lambda: hsmm.logz_backward(em, tk.C, tk.init, tk.trans, tk.lenp, tk.end,
+                                                                       tk.lengths_i32, tk.order, g, saved, trans_succ=tk.succ,
+                                                                       f64_state=xp))
+            timed(("weighted_feature_sums", i), lambda: hsmm.weighted_feature_sums(tk.X, d[3], tk.C, tk.lengths_i32))
+            timed(("viterbi", i), lambda: hsmm.viterbi_decode(em, tk.C, tk.init, tk.trans, tk.lenp, tk.end, offset,
+                                                              tk.lengths_i32, tk.order, tk.class_ids, want_score=False,
+                                                              trans_pred=tk.pred))
+            if rep == 0:
+                for n in names:
+                    launches[n] += 1
+    return {n: sum(v for (k, _), v in best.items() if k == n) for n in names}, launches
 
 
 # ---------------------------------------------------------------------------------------------

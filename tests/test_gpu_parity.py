@@ -509,3 +509,57 @@ def test_linear_window_flags_fall_back_to_log_domain(case):
         for k, v in mine.items():
             assert rel_err(v.cpu().numpy(), acc[k]) < 1e-4, (case, k, rel_err(v.cpu().numpy(), acc[k]), n_flagged)
     print(case, "flagged forward:", n_flagged, "backward:", int((bf > 0).sum()))
+
+
+VIT2_SHAPES = [
+    # (B, Tmax, C, K, chain, ends, em scale)
+    (16, 400, 23, 20, True, True, 3.0),   # vit2<20,1> sparse (flagship)
+    (16, 400, 13, 20, True, True, 12.0),  # vit2<10,2> sparse
+    (12, 300, 23, 20, False, False, 3.0),  # vit2<20,1> dense
+    (12, 300, 11, 20, False, False, 1.0),  # vit2<10,2> dense, many near ties
+    (8, 200, 5, 30, False, False, 3.0),   # vit2<13,4>
+    (8, 200, 16, 33, False, False, 3.0),  # vit2<25,2>, L = 32
+    (8, 150, 3, 30, False, False, 3.0),   # vit2<32,1>
+    (6, 12, 4, 40, False, False, 3.0),    # K clamped to the padded length
+]
+
+
+@pytest.mark.parametrize("shape", VIT2_SHAPES, ids=lambda s: "B%d_T%d_C%d_K%d_s%g" % (s[0], s[1], s[2], s[3], s[6]))
+def test_viterbi_deferred_argmax_identical_to_generic_kernel(shape):
+    """The deferred-arg-max kernel rebuilds the sweep's candidates bit for bit during the back-trace: spans, labels
+    and scores must be IDENTICAL to dp_forward_kernel<VIT> (hsmm_set_linear_window(0)), and match the oracle."""
+    import action_segmentation_b200 as pkg
+    B, Tmax, C, K, chain, ends, scale = shape
+    rng = np.random.default_rng(500 + C * 7 + K)
+    prob = random_problem(rng, B, Tmax, C, K, Tmin=1, chain=chain, ends=ends, scale=scale)
+    if chain:  # one video too short for the chain: no path through the sparse hint -> flagged -> generic kernel
+        prob["lengths"][2] = 3
+        end = np.full((B, C), O.BIG_NEG)
+        end[:, C - 1] = 0.0
+        prob["end"] = end
+    prob["lenp"] = O.clamp_len_table(prob["lenp"], Tmax)
+    K_eff = prob["lenp"].shape[0]
+    d = to_dev(prob)
+    sp = sparse_lists(prob) if chain else None
+    cid = torch.arange(100, 100 + C + 1, dtype=torch.int32, device="cuda")  # global class ids
+
+    def run():
+        return pkg.hsmm.viterbi_decode(d["em"], C, d["init"], d["trans"], d["lenp"], d["end"], None, d["lengths_i32"],
+                                       d["order"], class_ids=cid, trans_pred=None if sp is None else sp[0])
+    assert pkg._lib.dp_variant(C, K_eff, 0, chain).startswith("lin+")
+    try:
+        s1, l1, sc1 = run()
+        pkg._lib.set_linear_window(False)
+        s0, l0, sc0 = run()
+    finally:
+        pkg._lib.set_linear_window(True)
+    assert (s1 == s0).all() and (l1 == l0).all()
+    assert torch.allclose(sc1, sc0, rtol=1e-6, atol=1e-6)  # (the normaliser sum is grouped differently)
+    # against the oracle (local ids)
+    spans_local = torch.where(s1 >= 100, s1 - 100, s1).cpu().numpy()
+    feas = [b for b in range(B) if not (chain and prob["lengths"][b] < C)]
+    sub = dict(prob, em=prob["em"][feas], lengths=prob["lengths"][feas], end=None if prob["end"] is None else prob["end"][feas])
+    # long runs of one class can be cut into the same multiset of lengths in several orders with EXACTLY the same
+    # score (self-transitions), so the oracle's tie-break need not be ours: require optimality to fp32 rounding
+    # (fp64 score of the decoded path within 1e-6 relative of the oracle's best), not the identical path
+    check_viterbi_against_oracle(sub, spans_local[feas], sc1.cpu().numpy()[feas], tol=1e-6)
