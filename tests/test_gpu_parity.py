@@ -437,7 +437,7 @@ def test_linear_window_matches_log_domain_and_oracle(shape):
         lz0, g0, ff0, bf0 = _fwd_bwd(prob, d, sp, w)
     finally:
         pkg._lib.set_linear_window(True)
-    assert (ff0 < 2).all() and (bf0 == 0).all()
+    assert (ff0 < 2).all()  # (bflag is only written by the linear-window backward kernel)
     if K <= 32:
         # ordinary inputs with short windows are certified by the linear-window kernels: nothing goes to the fallback
         assert (ff1 < 2).all() and (bf1 == 0).all(), (ff1, bf1)

@@ -17,10 +17,16 @@ cat $OUT/${TAG}_bench_ref.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'hsmm|etc::|weighted_sums|dp_|emission' -c 600 --csv --log-file $OUT/${TAG}_launches.csv \
   python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-graph > $OUT/${TAG}_launches_bench.log 2>&1
 echo "ncu launches rc=$?"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:'dp_' -s 3 -c 3 -o $OUT/${TAG}_dp_sat \
+# full captures: summarised to CSV on the box (the .ncu-rep files are too large to bring back: gpurun_out is capped at 64 MiB)
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:'dp_lin|dp_vit2' -s 3 -c 3 -o /tmp/${TAG}_dp_sat \
   python tools/sat_profile.py > $OUT/${TAG}_ncu_sat.log 2>&1
 echo "ncu sat rc=$?"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:'dp_|emission_tc|weighted' -s 15 -c 10 -o $OUT/${TAG}_bench_top \
+ncu -i /tmp/${TAG}_dp_sat.ncu-rep --page raw --csv > $OUT/${TAG}_dp_sat_raw.csv 2>/dev/null
+for k in dp_lin_forward dp_lin_backward dp_vit2; do
+  ncu -i /tmp/${TAG}_dp_sat.ncu-rep --page source --csv --kernel-name regex:$k > $OUT/${TAG}_dp_sat_source_$k.csv 2>/dev/null
+done
+timeout 600 ncu --set full --clock-control none -k regex:'dp_lin|dp_vit2|emission_tc|weighted' -s 10 -c 10 -o /tmp/${TAG}_bench_top \
   python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-graph > $OUT/${TAG}_ncu_bench.log 2>&1
 echo "ncu bench rc=$?"
+ncu -i /tmp/${TAG}_bench_top.ncu-rep --page raw --csv > $OUT/${TAG}_bench_top_raw.csv 2>/dev/null
 ls -la $OUT

@@ -14,7 +14,7 @@ KEYS = ["Kernel Name", "Grid Size", "Block Size", "gpu__time_duration.sum", "dra
         "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__thread_inst_executed_per_inst_executed.ratio"]
 NAMES = {"dp_backward": "logz_backward", "dp_forward_kernel<(bool)0": "logz_forward", "dp_forward_kernel<(bool)1": "viterbi",
-         "dp_lin_forward": "logz_forward", "dp_lin_backward": "logz_backward", "dp_vit": "viterbi",
+         "dp_lin_forward": "logz_forward", "dp_lin_backward": "logz_backward", "dp_vit2": "viterbi",
          "emission_tc": "emission", "emission_kernel": "emission", "weighted_sums": "weighted_feature_sums"}
 
 
@@ -25,7 +25,10 @@ def to_bytes(v, unit):
 
 def main():
     rep, out = sys.argv[1], sys.argv[2]
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if rep.endswith(".csv"):  # already exported on the GPU box (ncu -i x.ncu-rep --page raw --csv)
+        raw = open(rep).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units = rows[0], rows[1]
     ix = {h: i for i, h in enumerate(hdr)}
@@ -45,8 +48,10 @@ def main():
                     traffic.setdefault(nm, []).append(t)
     if "--traffic" in sys.argv:
         path = sys.argv[sys.argv.index("--traffic") + 1]
-        json.dump({k: sum(v) / len(v) for k, v in traffic.items()} | {"_note": "mean dram bytes (read+write) per profiled launch, from " + rep},
-                  open(path, "w"), indent=1)
+        # one API call = the main kernel + (for the DP) the near-empty only-flagged fallback launch behind it:
+        # bytes per call = total bytes / number of launches that moved more than 1 MB
+        json.dump({k: sum(v) / max(1, sum(1 for t in v if t > 1e6)) for k, v in traffic.items()} |
+                  {"_note": "mean dram bytes (read+write) per profiled API call, from " + rep}, open(path, "w"), indent=1)
     print("wrote", out, {k: len(v) for k, v in traffic.items()})
 
 
