@@ -532,8 +532,9 @@ def main():
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_frame": bpf,
                 "kernel_ms": {k: round(v, 3) for k, v in kms.items()}, "launches_per_step": klaunch,
-                "step_achieved_gbs": step_bytes / (ms_per_step * 1e-3) / 1e9 * (1.0 if world == 1 else 1.0 / world),
-                "step_frac": step_bytes / (ms_per_step * 1e-3) / 1e9 / peak_gbs / (1.0 if world == 1 else world)}
+                # whole step against the same peak, per GPU (step_bytes counts this rank's frames)
+                "step_achieved_gbs": step_bytes / (ms_per_step * 1e-3) / 1e9,
+                "step_frac": step_bytes / (ms_per_step * 1e-3) / 1e9 / peak_gbs}
 
     # ---- end to end through the public API -----------------------------------------------------
     e2e = None
@@ -559,7 +560,7 @@ def main():
         tt = torch.tensor([dt], device=device, dtype=torch.float64)
         if world > 1:
             torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
-        e2e = {"value": frames_all / float(tt[0]), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+        e2e = {"value": frames_all / float(tt[0]), "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
                "ms_per_step": float(tt[0]) * 1e3, "steps": n_e2e, "h2d_gbs_achieved": h2d / float(tt[0]) / 1e9}
         del host
 
