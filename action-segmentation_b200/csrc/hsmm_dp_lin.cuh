@@ -187,9 +187,16 @@ __global__ void __launch_bounds__(128) dp_lin_forward_kernel(const DpParams p) {
         P[0] = (j == 0) ? (dead ? 0.0f : ex2(fminf(beta - rho, 100.0f))) : carry * fac;
         rref = rho;
         eprev = e;
+        // packed FMAs (FFMA2): two (class, length) elements per instruction, two independent accumulator pairs
         float sp[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
-        for (int i = 0; i < KR; ++i) sp[i & 3] = fmaf(P[i], pl[i], sp[i & 3]);
+        for (int i = 0; i + 1 < KR; i += 2) {
+            if ((i >> 1) & 1)
+                ffma2(sp[2], sp[3], P[i], P[i + 1], pl[i], pl[i + 1]);
+            else
+                ffma2(sp[0], sp[1], P[i], P[i + 1], pl[i], pl[i + 1]);
+        }
+        if (KR & 1) sp[0] = fmaf(P[KR - 1], pl[KR - 1], sp[0]);
         float s = slice_sum<S>((sp[0] + sp[1]) + (sp[2] + sp[3]));
         const bool live = valid && !dead;
         bad |= live && !(s > LIN_TINY);
@@ -276,9 +283,10 @@ __global__ void __launch_bounds__(128) dp_lin_forward_kernel(const DpParams p) {
 // backward (expected counts)
 // ---------------------------------------------------------------------------------------------
 template <int KR, int S, int TM>
-__global__ void __launch_bounds__(128) dp_lin_backward_kernel(const DpParams p) {
+__global__ void __launch_bounds__(128, (TM == 2 && KR <= 20) ? 4 : 1) dp_lin_backward_kernel(const DpParams p) {
     constexpr int CPW = Lay<S>::CPW;
     constexpr int CRR = Lay<S>::CRR;
+    constexpr int FB = 2;  // frames per prefetch group (four streams are prefetched: register budget)
     extern __shared__ __align__(16) float smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int C = p.C, L = p.L, ldc = p.ldc, Tmax = p.Tmax;
@@ -378,9 +386,9 @@ __global__ void __launch_bounds__(128) dp_lin_backward_kernel(const DpParams p) 
     const float* pd = p.fdelta + row0 + (T - 1);
     float* pdem = dem + (size_t)(T - 1) * ldc + c;
     const bool wr_dem = (j == 0 && c < ldc);
-    float enext[F], bnext[F], gnext[F], dnext[F];
+    float enext[FB], bnext[FB], gnext[FB], dnext[FB];
 #pragma unroll
-    for (int f = 0; f < F; ++f) {
+    for (int f = 0; f < FB; ++f) {
         const int nn = T - 1 - f;
         const bool ok = valid && nn > 0;
         enext[f] = (valid && nn >= 0) ? __ldg(pe - f * ldc) : 0.0f;
@@ -390,22 +398,22 @@ __global__ void __launch_bounds__(128) dp_lin_backward_kernel(const DpParams p) 
     }
 
 #pragma unroll 1
-    for (int n0 = T - 1; n0 >= 0; n0 -= F) {
-        float ecurv[F], bcurv[F], gcurv[F], dcurv[F];
+    for (int n0 = T - 1; n0 >= 0; n0 -= FB) {
+        float ecurv[FB], bcurv[FB], gcurv[FB], dcurv[FB];
 #pragma unroll
-        for (int f = 0; f < F; ++f) {
+        for (int f = 0; f < FB; ++f) {
             ecurv[f] = enext[f];
             bcurv[f] = bnext[f];
             gcurv[f] = gnext[f];
             dcurv[f] = dnext[f];
         }
-        pe -= F * ldc;
-        pb -= F * ldc;
-        pg -= F * ldc;
-        pd -= F;
+        pe -= FB * ldc;
+        pb -= FB * ldc;
+        pg -= FB * ldc;
+        pd -= FB;
 #pragma unroll
-        for (int f = 0; f < F; ++f) {
-            const int nn = n0 - F - f;
+        for (int f = 0; f < FB; ++f) {
+            const int nn = n0 - FB - f;
             const bool ok = valid && nn > 0;
             enext[f] = (valid && nn >= 0) ? __ldg(pe - f * ldc) : 0.0f;
             bnext[f] = ok ? __ldg(pb - f * ldc) : 0.0f;
@@ -413,7 +421,7 @@ __global__ void __launch_bounds__(128) dp_lin_backward_kernel(const DpParams p) 
             dnext[f] = (nn >= 1) ? __ldg(pd - f) : 0.0f;
         }
 #pragma unroll
-        for (int f = 0; f < F; ++f) {
+        for (int f = 0; f < FB; ++f) {
         const int n = n0 - f;
         if (n < 0) break;
         const float ecur = ecurv[f], bcur = bcurv[f], gcur = gcurv[f], gm_n = dcurv[f];
@@ -436,9 +444,16 @@ __global__ void __launch_bounds__(128) dp_lin_backward_kernel(const DpParams p) 
         const float coef0 = valid ? w * ex2(fminf((float)fb2, 100.0f)) : 0.0f;
         float sp[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
-        for (int i = 0; i < KR; ++i) {
-            sp[i & 3] = fmaf(Q[i], pl[i], sp[i & 3]);
-            El[i] = fmaf(Q[i], coef0, El[i]);
+        for (int i = 0; i + 1 < KR; i += 2) {  // packed FMAs (FFMA2)
+            if ((i >> 1) & 1)
+                ffma2(sp[2], sp[3], Q[i], Q[i + 1], pl[i], pl[i + 1]);
+            else
+                ffma2(sp[0], sp[1], Q[i], Q[i + 1], pl[i], pl[i + 1]);
+            ffma2(El[i], El[i + 1], Q[i], Q[i + 1], coef0, coef0);
+        }
+        if (KR & 1) {
+            sp[0] = fmaf(Q[KR - 1], pl[KR - 1], sp[0]);
+            El[KR - 1] = fmaf(Q[KR - 1], coef0, El[KR - 1]);
         }
         float s = slice_sum<S>((sp[0] + sp[1]) + (sp[2] + sp[3]));
         const bool live = valid && !dead;
