@@ -390,6 +390,98 @@ class SemiMarkovModule(nn.Module):
             return (score - logz).mean(), log_det.mean()
         return score.mean(), log_det.mean()
 
+    # ------------------------------------------------------------------------------------------
+    # closed-form EM (optional trainer beside the reference's Adam-on-logZ)
+    # ------------------------------------------------------------------------------------------
+    STAT_KEYS = ('wx', 'wsum', 'init', 'trans', 'len_num', 'len_den', 'logz', 'n')
+
+    def expected_statistics(self, features, lengths, valid_classes_per_instance,
+                            additional_allowed_ends_per_instance=None, constraints=None):
+        """E-step of one batch with the same kernels as `log_likelihood().backward()`: the expected counts the
+        reference only ever sees as gradients (semimarkov.py:284-286), in GLOBAL class layout so that batches of
+        different tasks (and ranks: `distributed.allreduce_stats(pack_statistics(...))`) add up.
+          wx (n_classes, D)   sum_t post[t,c] x_t      wsum (n_classes)  sum_t post[t,c]      (merged classes)
+          init (n_classes)    E[first segment is c]    trans (n_classes, n_classes) [to, from] expected transitions
+          len_num / len_den   sum_k k E_len[k,c] / sum_k E_len[k,c]                            (merged classes)
+          logz  sum of logZ_b   n  number of videos"""
+        valid_classes, C = self._valid_classes(valid_classes_per_instance)
+        dev = features.device
+        with torch.no_grad():
+            s = self._scores(features, lengths, valid_classes, additional_allowed_ends_per_instance)
+            em, rowterm, offset = hsmm.emission_scores(features, s['means'], s['cov_diag'], constraints, s['lengths_i32'])
+            xp = constraints is not None
+            pred, succ = (None, None) if s['sparse'] is None else s['sparse']
+            logz, saved = hsmm.logz_forward(em, C, s['init'], s['trans'], s['lenp'], s['end'], offset, s['lengths_i32'],
+                                            s['order'], trans_pred=pred, f64_state=xp)
+            g = torch.ones(features.size(0), device=dev)
+            d_init, d_trans, d_len, d_em = hsmm.logz_backward(em, C, s['init'], s['trans'], s['lenp'], s['end'],
+                                                             s['lengths_i32'], s['order'], g, saved, trans_succ=succ,
+                                                             f64_state=xp)
+            wx, wsum = hsmm.weighted_feature_sums(features, d_em, C, s['lengths_i32'])
+            tc = self._task_cache(valid_classes, dev)
+            ids = torch.arange(self.n_classes, device=dev) if tc['idx'] is None else tc['idx']
+            midx = tc['merged_idx']
+            n, D = self.n_classes, self.feature_dim
+            k = torch.arange(d_len.size(0), device=dev, dtype=torch.float32).unsqueeze(-1)
+            stats = dict(wx=torch.zeros(n, D, device=dev).index_add_(0, midx, wx),
+                         wsum=torch.zeros(n, device=dev).index_add_(0, midx, wsum),
+                         init=torch.zeros(n, device=dev).index_add_(0, ids, d_init),
+                         trans=torch.zeros(n, n, device=dev),
+                         len_num=torch.zeros(n, device=dev).index_add_(0, midx, (d_len * k).sum(0)),
+                         len_den=torch.zeros(n, device=dev).index_add_(0, midx, d_len.sum(0)),
+                         logz=logz.sum().to(torch.float32).reshape(1),
+                         n=torch.full((1,), float(features.size(0)), device=dev))
+            stats['trans'][ids.unsqueeze(1), ids.unsqueeze(0)] += d_trans
+        return stats
+
+    @classmethod
+    def pack_statistics(cls, stats):
+        return torch.cat([stats[k].reshape(-1) for k in cls.STAT_KEYS])
+
+    def unpack_statistics(self, buf):
+        n, D = self.n_classes, self.feature_dim
+        shapes = dict(wx=(n, D), wsum=(n,), init=(n,), trans=(n, n), len_num=(n,), len_den=(n,), logz=(1,), n=(1,))
+        out, off = {}, 0
+        for k in self.STAT_KEYS:
+            m = int(np.prod(shapes[k]))
+            out[k] = buf[off:off + m].view(*shapes[k])
+            off += m
+        return out
+
+    @staticmethod
+    def add_statistics(a, b):
+        return b if a is None else {k: a[k] + b[k] for k in a}
+
+    def em_update(self, stats, state_smoothing=0.0, length_smoothing=0.0, min_count=1e-6):
+        """Closed-form M-step from (summed) `expected_statistics`: class means = wx / wsum (tied diagonal covariance
+        stays fixed, as in the reference where `gaussian_cov` has requires_grad=False, semimarkov_modules.py:150-151),
+        Poisson rate = expected mean segment length, transition columns and initial distribution = normalised
+        expected counts over the unmasked entries.  Classes that received no mass keep their parameters.
+        Emission/length parameters live at the merged class ids."""
+        with torch.no_grad():
+            wsum = stats['wsum']
+            seen = wsum > min_count
+            means = stats['wx'] / wsum.clamp(min=min_count).unsqueeze(-1)
+            self.gaussian_means.data = torch.where(seen.unsqueeze(-1), means, self.gaussian_means.data)
+            lden = stats['len_den']
+            rate = (stats['len_num'] + length_smoothing) / (lden + length_smoothing).clamp(min=min_count)
+            self.poisson_log_rates.data = torch.where(lden > min_count, rate.clamp(min=1e-3).log(), self.poisson_log_rates.data)
+            tr = stats['trans'] + state_smoothing
+            if self.transition_constraints is not None:
+                tr = tr.masked_fill(self.transition_constraints, 0.0)
+            if not self.allow_self_transitions:
+                tr = tr.masked_fill(torch.eye(self.n_classes, device=tr.device).bool(), 0.0)
+            col = tr.sum(dim=0, keepdim=True)
+            new_t = torch.where(tr > 0, (tr / col.clamp(min=min_count)).clamp(min=1e-30).log(), torch.full_like(tr, -30.0))
+            self.transition_logits.data = torch.where(col > min_count, new_t, self.transition_logits.data)
+            ini = stats['init'] + state_smoothing
+            if self.init_constraints is not None:
+                ini = ini.masked_fill(self.init_constraints, 0.0)
+            tot = ini.sum()
+            if float(tot) > min_count:
+                self.init_logits.data = torch.where(ini > 0, (ini / tot).clamp(min=1e-30).log(), torch.full_like(ini, -30.0))
+        return float(stats['logz']) / max(1.0, float(stats['n']))
+
     def viterbi(self, features, lengths, valid_classes_per_instance, add_eos=True, use_mean_z=False,
                 additional_allowed_ends_per_instance=None, constraints=None, predict_single=False, return_elp=False,
                 return_labels=False, non_blocking=False):

@@ -563,3 +563,58 @@ def test_viterbi_deferred_argmax_identical_to_generic_kernel(shape):
     # score (self-transitions), so the oracle's tie-break need not be ours: require optimality to fp32 rounding
     # (fp64 score of the decoded path within 1e-6 relative of the oracle's best), not the identical path
     check_viterbi_against_oracle(sub, spans_local[feas], sc1.cpu().numpy()[feas], tol=1e-6)
+
+
+def test_em_statistics_and_closed_form_update():
+    """`expected_statistics` (the E-step behind SURVEY section 8f item 3) against the oracle's expected counts in global
+    class layout, and the closed-form M-step: every EM iteration must not decrease the mean log-likelihood."""
+    import action_segmentation_b200 as pkg
+    from oracle.module_oracle import ModuleOracle
+    from tests.golden.ref_import import RefArgs
+    torch.manual_seed(11)
+    B, T, D, C, K = 12, 120, 16, 7, 20
+    chain = {c: {c, c + 1} for c in range(C - 1)}
+    chain[C - 1] = {C - 1}
+    m = pkg.SemiMarkovModule(RefArgs(sm_max_span_length=K), C, D, allow_self_transitions=True, allowed_starts={0},
+                             allowed_transitions=chain, allowed_ends={C - 1}).cuda()
+    true_means = torch.randn(C, D, device="cuda") * 1.5
+    with torch.no_grad():
+        m.gaussian_means.copy_(true_means + 0.8 * torch.randn(C, D, device="cuda"))
+        m.poisson_log_rates.fill_(np.log(6.0))
+        m.transition_logits.normal_(0, 0.3)
+    lengths = torch.randint(60, T + 1, (B,))
+    lengths[0] = T
+    lab = torch.stack([torch.sort(torch.randint(0, C, (T,)))[0] for _ in range(B)]).cuda()
+    feats = true_means[lab] + torch.randn(B, T, D, device="cuda")
+    for i, n in enumerate(lengths):
+        feats[i, n:] = 0
+
+    stats = m.expected_statistics(feats, lengths, None)
+    params = {k: v.detach().cpu().numpy() for k, v in m.state_dict().items()}
+    mo = ModuleOracle(params, K, init_constraints=params["init_constraints"],
+                      transition_constraints=params["transition_constraints"], allowed_ends={C - 1})
+    r = mo.log_likelihood(feats.cpu().numpy(), lengths.numpy())
+    assert abs(float(stats["logz"]) / B - r["ll"]) <= 1e-5 * abs(r["ll"])
+    # per-video normalisation and frame bookkeeping
+    assert abs(float(stats["init"].sum()) - B) < 1e-3 * B
+    assert abs(float(stats["wsum"].sum()) - float(lengths.sum())) < 1e-4 * float(lengths.sum())
+    assert abs(float(stats["len_num"].sum()) - float(lengths.sum())) < 1e-4 * float(lengths.sum())
+    assert abs(float(stats["len_den"].sum()) - float(stats["trans"].sum()) - B) < 1e-3 * float(stats["len_den"].sum())
+    # d logZ / d means = (wx - wsum mu) / var must reproduce the oracle's gradient (mean over the batch)
+    var = torch.diagonal(m.gaussian_cov)
+    g_means = (stats["wx"] - stats["wsum"][:, None] * m.gaussian_means.detach()) / var[None, :] / B
+    assert rel_err(g_means.cpu().numpy(), r["grads"]["gaussian_means"]) < 1e-4
+    # pack / unpack (what one all-reduce carries)
+    back = m.unpack_statistics(m.pack_statistics(stats))
+    assert all(torch.equal(back[k], stats[k]) for k in m.STAT_KEYS)
+
+    lls = []
+    for it in range(4):
+        lls.append(m.em_update(m.expected_statistics(feats, lengths, None)))
+    final = float(m.expected_statistics(feats, lengths, None)["logz"]) / B
+    lls.append(final)
+    for a, b_ in zip(lls, lls[1:]):
+        assert b_ >= a - 1e-4 * abs(a), lls
+    assert lls[-1] > lls[0] + 1.0, lls
+    # the means moved towards the generating ones
+    assert float((m.gaussian_means.detach() - true_means).norm()) < 0.5 * float((0.8 * torch.ones(C, D)).norm())

@@ -143,3 +143,30 @@ def test_data_stand_in_batch_contract():
             assert batch["task_indices"][i].tolist() == order[batch["task_name"][i]]
         seen += B
     assert seen == 6
+
+
+def test_em_update_closed_form_on_given_statistics():
+    """M-step arithmetic (no kernels involved): normalised counts under the constraint masks, mean segment length,
+    class means = wx / wsum, untouched parameters for classes without mass."""
+    from tests.golden.ref_import import RefArgs
+    C, D = 4, 3
+    m = pkg.SemiMarkovModule(RefArgs(sm_max_span_length=10), C, D, allow_self_transitions=True, allowed_starts={0},
+                             allowed_transitions={0: {0, 1}, 1: {1, 2}, 2: {2, 3}, 3: {3}}, allowed_ends={3})
+    old_means = m.gaussian_means.detach().clone()
+    stats = dict(wx=torch.tensor([[2.0, 4.0, 6.0], [1.0, 1.0, 1.0], [0.0, 0.0, 0.0], [3.0, 0.0, 3.0]]),
+                 wsum=torch.tensor([2.0, 4.0, 0.0, 1.0]), init=torch.tensor([5.0, 0.0, 0.0, 0.0]),
+                 trans=torch.tensor([[3.0, 9.0, 0, 0], [1.0, 2.0, 0, 0], [0, 2.0, 0.0, 0], [0, 0, 1.0, 4.0]]),
+                 len_num=torch.tensor([12.0, 6.0, 0.0, 5.0]), len_den=torch.tensor([4.0, 3.0, 0.0, 1.0]),
+                 logz=torch.tensor([-50.0]), n=torch.tensor([5.0]))
+    ll = m.em_update(stats)
+    assert ll == -10.0
+    assert torch.allclose(m.gaussian_means[0], torch.tensor([1.0, 2.0, 3.0]))
+    assert torch.allclose(m.gaussian_means[2], old_means[2])  # no mass: untouched
+    assert torch.allclose(m.poisson_log_rates[:2].exp(), torch.tensor([3.0, 2.0]))
+    p = m.transition_log_probs(None).exp()  # [to, from], masked + normalised as the DP sees it
+    assert torch.allclose(p[:, 0], torch.tensor([0.75, 0.25, 0.0, 0.0]), atol=1e-6)  # the masked count 9.0 at [0,1] is ignored
+    assert torch.allclose(p[:, 1], torch.tensor([0.0, 0.5, 0.5, 0.0]), atol=1e-6)
+    assert torch.allclose(m.initial_log_probs(None).exp(), torch.tensor([1.0, 0.0, 0.0, 0.0]), atol=1e-6)
+    buf = m.pack_statistics(stats)
+    assert buf.numel() == C * D + C + C + C * C + C + C + 2
+    assert all(torch.equal(m.unpack_statistics(buf)[k], stats[k]) for k in m.STAT_KEYS)
