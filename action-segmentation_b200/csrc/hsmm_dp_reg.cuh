@@ -31,6 +31,8 @@
 //
 // The (B,T,K,C,C) potentials of the reference (semimarkov_modules.py:416-523) are never formed.
 #pragma once
+#include <stdlib.h>
+
 #include <type_traits>
 
 #include "hsmm_common.cuh"
