@@ -231,18 +231,55 @@ weighted_sums_kernel(const float* __restrict__ X, const float* __restrict__ wgt,
     for (int c = 0; c < CPT; ++c) acc[c][0] = acc[c][1] = acc[c][2] = acc[c][3] = 0.0f;
     float wsum = 0.0f;  // thread c < nc (of the d-block 0 CTAs) accumulates the column sums
 
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    // The class weights of the NEXT tile are fetched (float4 per thread, into registers) while the current tile streams
+    // its features: a plain load -> store-to-shared phase per tile left every warp of the CTA waiting on HBM latency
+    // in front of a barrier (40 % of the stall samples in ncu).
+    constexpr int NQ = CP / 4;                                       // float4 per frame
+    constexpr int NLD = (W_TF * NQ + W_THREADS - 1) / W_THREADS;     // float4 per thread and tile
+    float4 wreg[NLD];
+    auto next_active = [&](int tile) {
+        for (; tile < ntiles; tile += gridDim.x) {
+            const int b = tile / tiles_per_video;
+            if ((tile - b * tiles_per_video) * W_TF < lengths[b]) break;
+        }
+        return tile;
+    };
+    auto issue = [&](int tile) {
         const int b = tile / tiles_per_video;
         const int t0 = (tile - b * tiles_per_video) * W_TF;
-        const int T = lengths[b];
-        if (t0 >= T) continue;
-        const int nf = min(W_TF, T - t0);
+        const int nf = min(W_TF, lengths[b] - t0);
+#pragma unroll
+        for (int l = 0; l < NLD; ++l) {
+            const int i = tid + l * W_THREADS;
+            const int f = i / NQ, c0 = (i - f * NQ) * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < W_TF * NQ && f < nf && cb + c0 < ldc)
+                v = __ldg(reinterpret_cast<const float4*>(wgt + ((size_t)b * Tmax + t0 + f) * ldc + cb + c0));
+            if (c0 + 0 >= nc) v.x = 0.f;
+            if (c0 + 1 >= nc) v.y = 0.f;
+            if (c0 + 2 >= nc) v.z = 0.f;
+            if (c0 + 3 >= nc) v.w = 0.f;
+            wreg[l] = v;
+        }
+    };
+    int tile = next_active(blockIdx.x);
+    if (tile < ntiles) issue(tile);
+    while (tile < ntiles) {
+        const int b = tile / tiles_per_video;
+        const int t0 = (tile - b * tiles_per_video) * W_TF;
+        const int nf = min(W_TF, lengths[b] - t0);
         __syncthreads();
-        for (int i = tid; i < W_TF * CP; i += W_THREADS) {
-            const int f = i / CP, c = i - f * CP;
-            Ws[f][c] = (f < nf && c < nc) ? __ldg(wgt + ((size_t)b * Tmax + t0 + f) * ldc + cb + c) : 0.0f;
+#pragma unroll
+        for (int l = 0; l < NLD; ++l) {
+            const int i = tid + l * W_THREADS;
+            if (i < W_TF * NQ) {
+                const int f = i / NQ, c0 = (i - f * NQ) * 4;
+                *reinterpret_cast<float4*>(&Ws[f][c0]) = wreg[l];
+            }
         }
         __syncthreads();
+        const int nxt = next_active(tile + gridDim.x);
+        if (nxt < ntiles) issue(nxt);
         if (blockIdx.y == 0 && tid < nc) {
             for (int f = 0; f < nf; ++f) wsum += Ws[f][tid];
         }
@@ -273,6 +310,7 @@ weighted_sums_kernel(const float* __restrict__ X, const float* __restrict__ wgt,
                 }
             }
         }
+        tile = nxt;
     }
     // reduce the frame phases through shared memory (one class row per group at a time), one atomic per entry
 #pragma unroll
@@ -348,7 +386,7 @@ weighted_sums_generic_kernel(const float* __restrict__ X, const float* __restric
 
 int launch_weighted_sums(const float* X, const float* wgt, int ldc, const int32_t* lengths, int B, int Tmax, int D, int C,
                          float* out_wx, float* out_wsum, int num_sms, cudaStream_t st) {
-    if (D % 4 != 0 || (reinterpret_cast<uintptr_t>(X) & 15)) {
+    if (D % 4 != 0 || (reinterpret_cast<uintptr_t>(X) & 15) || ldc % 4 != 0 || (reinterpret_cast<uintptr_t>(wgt) & 15)) {
         const int tpv = (Tmax + 31) / 32;
         int grid = num_sms * 4;
         if (grid > B * tpv) grid = B * tpv;

@@ -142,7 +142,8 @@ emission_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
     constexpr int NPAD = 16 * NB;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // carve: [W: nchunk x (big NPAD x 128 B, small NPAD x 128 B)] [stages] [bias NPAD] [inv_var nchunk*32] [barriers]
-    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // (offset arithmetic on the __shared__ symbol keeps the address space visible to the compiler: LDS/STS, not generic LD/ST)
+    uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* w_s = base;
     const int w_chunk_bytes = 2 * NPAD * 128;
     uint8_t* st_s = w_s + (size_t)p.nchunk * w_chunk_bytes;
