@@ -14,9 +14,10 @@
 //   warp 0      TMA producer: X chunks of 32 floats (one 128-byte swizzle row per frame) into a ring
 //   warp 1      MMA issuer (one lane) + TMEM allocation; 2 accumulators of NPAD columns (double buffer)
 //   warps 2..5  "converters": split the landed chunk into big/small in place (+ the row term
-//               -0.5 sum x^2/var), then the epilogue of the PREVIOUS tile (TMEM -> registers: bias,
-//               penalty, per-frame shift, row term, f64 per-video offset) while the tensor core works on
-//               the current one.  Thread <-> frame, which is also the TMEM lane mapping of tcgen05.ld.
+//               -0.5 sum x^2/var, handed to the epilogue warps through shared memory).  Thread <-> frame.
+//   warps 6..9  epilogue (TMEM -> registers: bias, penalty, per-frame shift, row term, f64 per-video offset),
+//               concurrently with the conversion of the following tiles.  Thread <-> frame, which is also the
+//               TMEM lane mapping of tcgen05.ld (lane quarter = warp % 4).
 // Tiles that lie entirely in the zero padding behind a video are never loaded.
 #include <cuda.h>
 
@@ -30,7 +31,7 @@ constexpr int TILE_M = 128;       // frames per tile = UMMA M
 constexpr int KC = 32;            // floats per chunk = one 128-byte swizzle row
 constexpr int CHUNK_BYTES = TILE_M * KC * 4;  // 16 KB
 constexpr int STAGE_BYTES = 2 * CHUNK_BYTES;  // big + small
-constexpr int THREADS = 192;
+constexpr int THREADS = 320;
 constexpr int ACC_STRIDE = 64;    // TMEM columns between the two accumulators
 constexpr int TMEM_COLS = 128;
 constexpr int MAX_STAGES = 6;
@@ -143,7 +144,8 @@ emission_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // carve: [W: nchunk x (big NPAD x 128 B, small NPAD x 128 B)] [stages] [bias NPAD] [inv_var nchunk*32] [barriers]
     // (offset arithmetic on the __shared__ symbol keeps the address space visible to the compiler: LDS/STS, not generic LD/ST)
-    uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* base = smem_raw;  // 1024-byte aligned by declaration (the 128-byte swizzle atoms need it)
+    if (smem_u32(smem_raw) & 1023u) __trap();
     uint8_t* w_s = base;
     const int w_chunk_bytes = 2 * NPAD * 128;
     uint8_t* st_s = w_s + (size_t)p.nchunk * w_chunk_bytes;
@@ -156,7 +158,10 @@ emission_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
     uint64_t* tfull = empty + MAX_STAGES;      // MMA -> epilogue   [2]
     uint64_t* tempty = tfull + 2;              // epilogue -> MMA   [2]
     uint64_t* wbar = tempty + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
+    uint64_t* rfull = wbar + 1;                // converters -> epilogue: row terms of a tile   [2]
+    uint64_t* rempty = rfull + 2;              // epilogue -> converters                         [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rempty + 2);
+    float* rowsq_s = reinterpret_cast<float*>(tmem_slot + 4);  // [2][128]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int klast = (p.D - (p.nchunk - 1) * KC + 7) / 8;  // k-steps (of 8) in the last chunk
@@ -170,6 +175,8 @@ emission_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
         for (int a = 0; a < 2; ++a) {
             mbar_init(tfull + a, 1);
             mbar_init(tempty + a, 128);
+            mbar_init(rfull + a, 128);
+            mbar_init(rempty + a, 128);
         }
         mbar_init(wbar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -180,8 +187,8 @@ emission_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (warp >= 2) {
-        for (int i = threadIdx.x - 64; i < NPAD; i += 128) bias_s[i] = (i < p.C) ? p.bias[i] : 0.0f;
-        for (int i = threadIdx.x - 64; i < p.nchunk * KC; i += 128) iv_s[i] = (i < p.D) ? p.inv_var[i] : 0.0f;
+        for (int i = threadIdx.x - 64; i < NPAD; i += THREADS - 64) bias_s[i] = (i < p.C) ? p.bias[i] : 0.0f;
+        for (int i = threadIdx.x - 64; i < p.nchunk * KC; i += THREADS - 64) iv_s[i] = (i < p.D) ? p.inv_var[i] : 0.0f;
     }
     tc_fence_before();
     __syncthreads();
@@ -254,22 +261,66 @@ emission_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
                 }
             }
         }
-    } else {
-        // ===================== converters + epilogue (128 threads, thread <-> frame) =====================
-        const int q = warp & 3;              // TMEM lane quarter this warp may read
-        const int r = q * 32 + lane;         // row inside the tile
-        const long long total_rows = (long long)p.B * p.Tmax;
-        const float row_const = __ldg(p.row_const);
+    } else if (warp < 6) {
+        // ===================== converters (128 threads, thread <-> frame) =====================
+        const int r = (warp & 3) * 32 + lane;  // row inside the tile
         int st = 0;
         uint32_t ph = 0;
         int acc = 0;
         uint32_t accph = 0;
-        // pending epilogue (previous tile)
-        int pend_tile = -1;
-        bool pend_active = false;
-        float pend_rowsq = 0.0f;
-        int pend_acc = 0;
-        uint32_t pend_accph = 0;
+        for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+            if (!tile_active(p, tile)) continue;
+            float rowsq = 0.0f;
+            for (int ch = 0; ch < p.nchunk; ++ch) {
+                mbar_wait(full + st, ph);
+                uint8_t* xb = st_s + (size_t)st * STAGE_BYTES + (size_t)r * 128;
+                uint8_t* xs = xb + CHUNK_BYTES;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int pj = (i + r) & 7;            // physical 16-byte slot (rotated: conflict-free)
+                    const int lj = pj ^ (r & 7);           // logical slot under the 128-byte swizzle
+                    float4 x = *reinterpret_cast<float4*>(xb + pj * 16);
+                    const float4 iv = *reinterpret_cast<const float4*>(iv_s + ch * KC + lj * 4);
+                    rowsq = fmaf(x.x * x.x, iv.x, rowsq);
+                    rowsq = fmaf(x.y * x.y, iv.y, rowsq);
+                    rowsq = fmaf(x.z * x.z, iv.z, rowsq);
+                    rowsq = fmaf(x.w * x.w, iv.w, rowsq);
+                    float4 big, sml;
+                    big.x = __uint_as_float(__float_as_uint(x.x) & TF32_MASK);
+                    big.y = __uint_as_float(__float_as_uint(x.y) & TF32_MASK);
+                    big.z = __uint_as_float(__float_as_uint(x.z) & TF32_MASK);
+                    big.w = __uint_as_float(__float_as_uint(x.w) & TF32_MASK);
+                    sml.x = x.x - big.x;
+                    sml.y = x.y - big.y;
+                    sml.z = x.z - big.z;
+                    sml.w = x.w - big.w;
+                    *reinterpret_cast<float4*>(xb + pj * 16) = big;
+                    *reinterpret_cast<float4*>(xs + pj * 16) = sml;
+                }
+                fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
+                mbar_arrive(conv + st);
+                if (++st == p.nstage) {
+                    st = 0;
+                    ph ^= 1;
+                }
+            }
+            // the row terms of this tile go to the epilogue warps (slot = accumulator parity)
+            mbar_wait(rempty + acc, accph ^ 1);
+            rowsq_s[acc * TILE_M + r] = rowsq;
+            mbar_arrive(rfull + acc);
+            if (++acc == 2) {
+                acc = 0;
+                accph ^= 1;
+            }
+        }
+    } else {
+        // ===================== epilogue (128 threads, thread <-> frame) =====================
+        const int q = warp & 3;              // TMEM lane quarter this warp may read
+        const int r = q * 32 + lane;         // row inside the tile
+        const long long total_rows = (long long)p.B * p.Tmax;
+        const float row_const = __ldg(p.row_const);
+        int acc = 0;
+        uint32_t accph = 0;
 
         auto epilogue = [&](int tile, bool active, float rowsq, int a, uint32_t aph) {
             const long long row = (long long)tile * TILE_M + r;
@@ -344,52 +395,16 @@ emission_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
             const bool active = tile_active(p, tile);
             float rowsq = 0.0f;
             if (active) {
-                for (int ch = 0; ch < p.nchunk; ++ch) {
-                    mbar_wait(full + st, ph);
-                    uint8_t* xb = st_s + (size_t)st * STAGE_BYTES + (size_t)r * 128;
-                    uint8_t* xs = xb + CHUNK_BYTES;
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int pj = (i + r) & 7;            // physical 16-byte slot (rotated: conflict-free)
-                        const int lj = pj ^ (r & 7);           // logical slot under the 128-byte swizzle
-                        float4 x = *reinterpret_cast<float4*>(xb + pj * 16);
-                        const float4 iv = *reinterpret_cast<const float4*>(iv_s + ch * KC + lj * 4);
-                        rowsq = fmaf(x.x * x.x, iv.x, rowsq);
-                        rowsq = fmaf(x.y * x.y, iv.y, rowsq);
-                        rowsq = fmaf(x.z * x.z, iv.z, rowsq);
-                        rowsq = fmaf(x.w * x.w, iv.w, rowsq);
-                        float4 big, sml;
-                        big.x = __uint_as_float(__float_as_uint(x.x) & TF32_MASK);
-                        big.y = __uint_as_float(__float_as_uint(x.y) & TF32_MASK);
-                        big.z = __uint_as_float(__float_as_uint(x.z) & TF32_MASK);
-                        big.w = __uint_as_float(__float_as_uint(x.w) & TF32_MASK);
-                        sml.x = x.x - big.x;
-                        sml.y = x.y - big.y;
-                        sml.z = x.z - big.z;
-                        sml.w = x.w - big.w;
-                        *reinterpret_cast<float4*>(xb + pj * 16) = big;
-                        *reinterpret_cast<float4*>(xs + pj * 16) = sml;
-                    }
-                    fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
-                    mbar_arrive(conv + st);
-                    if (++st == p.nstage) {
-                        st = 0;
-                        ph ^= 1;
-                    }
-                }
+                mbar_wait(rfull + acc, accph);
+                rowsq = rowsq_s[acc * TILE_M + r];
+                mbar_arrive(rempty + acc);
             }
-            if (pend_tile >= 0) epilogue(pend_tile, pend_active, pend_rowsq, pend_acc, pend_accph);
-            pend_tile = tile;
-            pend_active = active;
-            pend_rowsq = rowsq;
-            pend_acc = acc;
-            pend_accph = accph;
+            epilogue(tile, active, rowsq, acc, accph);
             if (active && ++acc == 2) {
                 acc = 0;
                 accph ^= 1;
             }
         }
-        if (pend_tile >= 0) epilogue(pend_tile, pend_active, pend_rowsq, pend_acc, pend_accph);
     }
 
     tc_fence_before();
@@ -450,8 +465,8 @@ static bool plan(int D, int C, Plan* pl) {
     if (C > 64 || D % 4 != 0 || D < 4) return false;
     pl->npad = (C + 15) / 16 * 16;
     pl->nchunk = (D + KC - 1) / KC;
-    const size_t fixed = 1024 + (size_t)pl->nchunk * 2 * pl->npad * 128 + (size_t)(pl->npad + pl->nchunk * KC) * 4 +
-                         (3 * MAX_STAGES + 5) * 8 + 16;
+    const size_t fixed = (size_t)pl->nchunk * 2 * pl->npad * 128 + (size_t)(pl->npad + pl->nchunk * KC) * 4 +
+                         (3 * MAX_STAGES + 9) * 8 + 16 + 2 * TILE_M * 4;
     const size_t cap = 227 * 1024;
     if (fixed + 2 * (size_t)STAGE_BYTES > cap) return false;
     int ns = (int)((cap - fixed) / STAGE_BYTES);
