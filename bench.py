@@ -137,8 +137,9 @@ def make_task(t, steps, V, D, K, tmin, tmax, narration, gen, device):
 
 def make_workload(args, rank, device):
     gen = torch.Generator().manual_seed(args.seed + rank)
-    return [make_task(t, s, args.videos_per_task, args.feature_dim, args.max_span, args.tmin, args.tmax, args.narration,
-                      gen, device) for t, s in enumerate(CROSSTASK_STEPS)]
+    tasks = [make_task(t, s, args.videos_per_task, args.feature_dim, args.max_span, args.tmin, args.tmax, args.narration,
+                       gen, device) for t, s in enumerate(CROSSTASK_STEPS)]
+    return tasks
 
 
 def packed_layout(tasks):
