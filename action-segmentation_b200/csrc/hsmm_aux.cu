@@ -224,7 +224,6 @@ weighted_sums_kernel(const float* __restrict__ X, const float* __restrict__ wgt,
     const int cb = blockIdx.z * CP;                   // first class of this CTA
     const int nc = min(CP, C - cb);
     const bool dok = d0 < D;                          // D % 4 == 0 on this path
-    const int ntiles = B * tiles_per_video;
 
     float acc[CPT][4];
 #pragma unroll
@@ -237,24 +236,25 @@ weighted_sums_kernel(const float* __restrict__ X, const float* __restrict__ wgt,
     constexpr int NQ = CP / 4;                                       // float4 per frame
     constexpr int NLD = (W_TF * NQ + W_THREADS - 1) / W_THREADS;     // float4 per thread and tile
     float4 wreg[NLD];
-    auto next_active = [&](int tile) {
-        for (; tile < ntiles; tile += gridDim.x) {
-            const int b = tile / tiles_per_video;
-            if ((tile - b * tiles_per_video) * W_TF < lengths[b]) break;
-        }
-        return tile;
+    // live tiles only, dealt round-robin to the persistent CTAs (TileCursor, hsmm_common.cuh)
+    TileCursor cur;
+    struct Tile { int b, t0, nf; };
+    auto locate = [&](int g, Tile& tl) {
+        int vb, j, vlen;
+        if (!cur.locate(g, lengths, B, W_TF, vb, j, vlen)) return false;
+        tl.b = vb;
+        tl.t0 = j * W_TF;
+        tl.nf = min(W_TF, vlen - tl.t0);
+        return true;
     };
-    auto issue = [&](int tile) {
-        const int b = tile / tiles_per_video;
-        const int t0 = (tile - b * tiles_per_video) * W_TF;
-        const int nf = min(W_TF, lengths[b] - t0);
+    auto issue = [&](const Tile& tl) {
 #pragma unroll
         for (int l = 0; l < NLD; ++l) {
             const int i = tid + l * W_THREADS;
             const int f = i / NQ, c0 = (i - f * NQ) * 4;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (i < W_TF * NQ && f < nf && cb + c0 < ldc)
-                v = __ldg(reinterpret_cast<const float4*>(wgt + ((size_t)b * Tmax + t0 + f) * ldc + cb + c0));
+            if (i < W_TF * NQ && f < tl.nf && cb + c0 < ldc)
+                v = __ldg(reinterpret_cast<const float4*>(wgt + ((size_t)tl.b * Tmax + tl.t0 + f) * ldc + cb + c0));
             if (c0 + 0 >= nc) v.x = 0.f;
             if (c0 + 1 >= nc) v.y = 0.f;
             if (c0 + 2 >= nc) v.z = 0.f;
@@ -262,12 +262,12 @@ weighted_sums_kernel(const float* __restrict__ X, const float* __restrict__ wgt,
             wreg[l] = v;
         }
     };
-    int tile = next_active(blockIdx.x);
-    if (tile < ntiles) issue(tile);
-    while (tile < ntiles) {
-        const int b = tile / tiles_per_video;
-        const int t0 = (tile - b * tiles_per_video) * W_TF;
-        const int nf = min(W_TF, lengths[b] - t0);
+    int g = blockIdx.x;
+    Tile tl, nx;
+    bool have = locate(g, tl);
+    if (have) issue(tl);
+    while (have) {
+        const int b = tl.b, t0 = tl.t0, nf = tl.nf;
         __syncthreads();
 #pragma unroll
         for (int l = 0; l < NLD; ++l) {
@@ -278,8 +278,9 @@ weighted_sums_kernel(const float* __restrict__ X, const float* __restrict__ wgt,
             }
         }
         __syncthreads();
-        const int nxt = next_active(tile + gridDim.x);
-        if (nxt < ntiles) issue(nxt);
+        g += gridDim.x;
+        const bool have_next = locate(g, nx);
+        if (have_next) issue(nx);
         if (blockIdx.y == 0 && tid < nc) {
             for (int f = 0; f < nf; ++f) wsum += Ws[f][tid];
         }
@@ -310,7 +311,8 @@ weighted_sums_kernel(const float* __restrict__ X, const float* __restrict__ wgt,
                 }
             }
         }
-        tile = nxt;
+        tl = nx;
+        have = have_next;
     }
     // reduce the frame phases through shared memory (one class row per group at a time), one atomic per entry
 #pragma unroll

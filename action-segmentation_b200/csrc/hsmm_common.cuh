@@ -98,6 +98,55 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
+
+// ---- balanced enumeration of the frame tiles of a ragged batch ------------------------------------
+// Video b contributes ceil(len_b / TF) tiles of TF frames; tile g of the batch-wide enumeration is tile j of video
+// vb.  A persistent CTA takes g = blockIdx.x, blockIdx.x + gridDim.x, ...: every CTA gets the same number of LIVE
+// tiles (+-1), whereas striding over the padded (B x ceil(Tmax/TF)) grid and skipping the dead tiles leaves the CTAs
+// with binomially distributed work (measured: SMs idle for 25 % of the kernel on U[1000,3000]-frame videos).
+// The cursor is warp-cooperative and monotone: all 32 lanes call locate() with the same, non-decreasing g; it walks
+// the lengths 32 videos at a time (one coalesced load + a shuffle scan per window).
+struct TileCursor {
+    int b0 = 0;     // first video of the current window of 32
+    int base = 0;   // tiles before video b0
+    int incl = 0;   // lane i: inclusive tile count of videos b0 .. b0+i
+    int len = 0;    // lane i: length of video b0+i (0 past the batch)
+    bool loaded = false;
+
+    __device__ __forceinline__ void load(const int32_t* __restrict__ lengths, int B, int TF) {
+        const int lane = threadIdx.x & 31;
+        const int b = b0 + lane;
+        len = (b < B) ? max(lengths[b], 0) : 0;
+        int v = (len + TF - 1) / TF;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int o = __shfl_up_sync(FULL, v, off);
+            if (lane >= off) v += o;
+        }
+        incl = v;
+        loaded = true;
+    }
+    // false when g is past the last tile of the batch
+    __device__ __forceinline__ bool locate(int g, const int32_t* __restrict__ lengths, int B, int TF, int& vb, int& j, int& vlen) {
+        if (!loaded) load(lengths, B, TF);
+        for (;;) {
+            if (b0 >= B) return false;
+            const int tot = __shfl_sync(FULL, incl, 31);
+            if (g < base + tot) break;
+            base += tot;
+            b0 += 32;
+            load(lengths, B, TF);
+        }
+        const unsigned m = __ballot_sync(FULL, g < base + incl);
+        const int l = __ffs(m) - 1;
+        const int incl_l = __shfl_sync(FULL, incl, l);
+        vlen = __shfl_sync(FULL, len, l);
+        vb = b0 + l;
+        j = g - base - (incl_l - (vlen + TF - 1) / TF);
+        return true;
+    }
+};
+
 // ---- DP parameter block -------------------------------------------------------------------
 struct DpParams {
     // inputs

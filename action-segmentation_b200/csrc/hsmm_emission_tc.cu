@@ -13,13 +13,19 @@
 // Persistent CTAs (one per SM), tile = 128 consecutive rows of the flattened (B*Tmax, D) feature matrix:
 //   warp 0      TMA producer: X chunks of 32 floats (one 128-byte swizzle row per frame) into a ring
 //   warp 1      MMA issuer (one lane) + TMEM allocation; 2 accumulators of NPAD columns (double buffer)
-//   warps 2..5  "converters": split the landed chunk into big/small in place (+ the row term
-//               -0.5 sum x^2/var, handed to the epilogue warps through shared memory).  Thread <-> frame.
-//   warps 6..9  epilogue (TMEM -> registers: bias, penalty, per-frame shift, row term, f64 per-video offset),
+//   warps 2..9  "converters", two groups of four warps that take alternate chunks of the ring: split the landed
+//               chunk into big/small in place (+ this group's part of the row term -0.5 sum x^2/var, handed to
+//               the epilogue warps through shared memory).  Thread <-> frame; all eight 16-byte loads of a row are
+//               issued before the first store (the swizzled slots alias for the compiler, so interleaved
+//               load/store code serialises on the shared-memory latency).
+//   warps 10..13 epilogue (TMEM -> registers: bias, penalty, per-frame shift, row term, f64 per-video offset),
 //               concurrently with the conversion of the following tiles.  Thread <-> frame, which is also the
 //               TMEM lane mapping of tcgen05.ld (lane quarter = warp % 4).
-// Tiles that lie entirely in the zero padding behind a video are never loaded.
+// A tile is 128 consecutive frames of ONE video (the last tile of a video runs into the padding / the next video's
+// rows, which are scored and dropped); only live tiles exist and they are dealt round-robin to the CTAs (TileCursor).
 #include <cuda.h>
+
+#include <cstdlib>
 
 #include "hsmm_common.cuh"
 
@@ -31,7 +37,8 @@ constexpr int TILE_M = 128;       // frames per tile = UMMA M
 constexpr int KC = 32;            // floats per chunk = one 128-byte swizzle row
 constexpr int CHUNK_BYTES = TILE_M * KC * 4;  // 16 KB
 constexpr int STAGE_BYTES = 2 * CHUNK_BYTES;  // big + small
-constexpr int THREADS = 320;
+constexpr int CONV_GROUPS = 2;   // converter groups (4 warps each) compiled in; Params::cgroups of them take alternate chunks
+constexpr int THREADS = 64 + 128 * CONV_GROUPS + 128;
 constexpr int ACC_STRIDE = 64;    // TMEM columns between the two accumulators
 constexpr int TMEM_COLS = 128;
 constexpr int MAX_STAGES = 6;
@@ -115,27 +122,13 @@ struct Params {
     float* rowterm;
     double* offset;
     const float* row_const;  // device scalar
+    int exp;                 // HSMM_ETC_EXP timing experiments (results invalid when != 0): 1 no conversion, 2 no MMA, 4 no stores
+    int cgroups;             // converter groups in use (1 when shared memory is tight, else CONV_GROUPS)
     int B, Tmax, D, C, ldc;
     int npad;     // classes padded to a multiple of 16 (UMMA N)
     int nchunk;   // ceil(D / 32)
     int nstage;   // ring depth
-    int ntiles;   // ceil(B*Tmax / 128)
 };
-
-// does the tile [r0, r0+128) of the flattened rows contain a frame of a video (t < length)?
-__device__ __forceinline__ bool tile_active(const Params& p, int tile) {
-    const long long r0 = (long long)tile * TILE_M;
-    const long long r1 = min(r0 + TILE_M, (long long)p.B * p.Tmax);
-    int b = (int)(r0 / p.Tmax);
-    long long start = r0;
-    while (start < r1) {
-        const int t = (int)(start - (long long)b * p.Tmax);
-        if (t < p.lengths[b]) return true;
-        ++b;
-        start = (long long)b * p.Tmax;
-    }
-    return false;
-}
 
 template <int NB>  // NPAD = 16 * NB
 __global__ void __launch_bounds__(THREADS, 1)
@@ -161,7 +154,7 @@ emission_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
     uint64_t* rfull = wbar + 1;                // converters -> epilogue: row terms of a tile   [2]
     uint64_t* rempty = rfull + 2;              // epilogue -> converters                         [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rempty + 2);
-    float* rowsq_s = reinterpret_cast<float*>(tmem_slot + 4);  // [2][128]
+    float* rowsq_s = reinterpret_cast<float*>(tmem_slot + 4);  // [2][CONV_GROUPS][128]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int klast = (p.D - (p.nchunk - 1) * KC + 7) / 8;  // k-steps (of 8) in the last chunk
@@ -175,7 +168,7 @@ emission_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
         for (int a = 0; a < 2; ++a) {
             mbar_init(tfull + a, 1);
             mbar_init(tempty + a, 128);
-            mbar_init(rfull + a, 128);
+            mbar_init(rfull + a, 128 * p.cgroups);
             mbar_init(rempty + a, 128);
         }
         mbar_init(wbar, 1);
@@ -195,6 +188,8 @@ emission_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    TileCursor cur;   // every warp walks the same enumeration of live tiles
+    int vb, vj, vlen;
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
@@ -203,32 +198,36 @@ emission_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
                 tma_load_2d(w_s + (size_t)ch * w_chunk_bytes, &tmap_w, wbar, ch * KC, 0);
                 tma_load_2d(w_s + (size_t)ch * w_chunk_bytes + NPAD * 128, &tmap_w, wbar, ch * KC, NPAD);
             }
-            int st = 0;
-            uint32_t ph = 0;
-            for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-                if (!tile_active(p, tile)) continue;
+        }
+        int st = 0;
+        uint32_t ph = 0;
+        for (int g = blockIdx.x; cur.locate(g, p.lengths, p.B, TILE_M, vb, vj, vlen); g += gridDim.x) {
+            if (lane == 0) {
+                const int row0 = vb * p.Tmax + vj * TILE_M;
                 for (int ch = 0; ch < p.nchunk; ++ch) {
                     mbar_wait(empty + st, ph ^ 1);
                     mbar_arrive_expect_tx(full + st, CHUNK_BYTES);
-                    tma_load_2d(st_s + (size_t)st * STAGE_BYTES, &tmap_x, full + st, ch * KC, tile * TILE_M);
+                    tma_load_2d(st_s + (size_t)st * STAGE_BYTES, &tmap_x, full + st, ch * KC, row0);
                     if (++st == p.nstage) {
                         st = 0;
                         ph ^= 1;
                     }
                 }
             }
+            st = __shfl_sync(FULL, st, 0);
+            ph = __shfl_sync(FULL, ph, 0);
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NPAD >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
-            mbar_wait(wbar, 0);
-            int st = 0;
-            uint32_t ph = 0;
-            int acc = 0;
-            uint32_t accph = 0;
-            for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-                if (!tile_active(p, tile)) continue;
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NPAD >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+        if (lane == 0) mbar_wait(wbar, 0);
+        __syncwarp();
+        int st = 0;
+        uint32_t ph = 0;
+        int acc = 0;
+        uint32_t accph = 0;
+        for (int g = blockIdx.x; cur.locate(g, p.lengths, p.B, TILE_M, vb, vj, vlen); g += gridDim.x) {
+            if (lane == 0) {
                 mbar_wait(tempty + acc, accph ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * ACC_STRIDE;
@@ -241,7 +240,7 @@ emission_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
                     const uint32_t wb = smem_u32(w_s + (size_t)ch * w_chunk_bytes);
                     const uint32_t ws = wb + NPAD * 128;
                     const int ksteps = (ch == p.nchunk - 1) ? klast : 4;
-                    for (int ks = 0; ks < ksteps; ++ks) {
+                    for (int ks = 0; ks < ksteps && !(p.exp & 2); ++ks) {
                         const uint32_t ko = ks * 32;  // 8 tf32 = 32 bytes inside the 128-byte swizzle row
                         tc_mma_tf32(d_tmem, smem_desc_sw128(xs + ko), smem_desc_sw128(wb + ko), idesc, accum);
                         accum = 1;
@@ -260,53 +259,74 @@ emission_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
                     accph ^= 1;
                 }
             }
+            st = __shfl_sync(FULL, st, 0);
+            ph = __shfl_sync(FULL, ph, 0);
+            acc = __shfl_sync(FULL, acc, 0);
+            accph = __shfl_sync(FULL, accph, 0);
         }
-    } else if (warp < 6) {
-        // ===================== converters (128 threads, thread <-> frame) =====================
-        const int r = (warp & 3) * 32 + lane;  // row inside the tile
+    } else if (warp < 2 + 4 * CONV_GROUPS) {
+        // ===================== converters (CONV_GROUPS x 128 threads, thread <-> frame) =====================
+        const int grp = (warp - 2) >> 2;       // this group converts the chunks with (running chunk index % cgroups) == grp
+        if (grp >= p.cgroups) goto done;
+        const int r = ((warp - 2) & 3) * 32 + lane;  // row inside the tile
         int st = 0;
         uint32_t ph = 0;
         int acc = 0;
         uint32_t accph = 0;
-        for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-            if (!tile_active(p, tile)) continue;
+        int turn = 0;                           // running chunk index modulo CONV_GROUPS
+        for (int g = blockIdx.x; cur.locate(g, p.lengths, p.B, TILE_M, vb, vj, vlen); g += gridDim.x) {
             float rowsq = 0.0f;
             for (int ch = 0; ch < p.nchunk; ++ch) {
-                mbar_wait(full + st, ph);
-                uint8_t* xb = st_s + (size_t)st * STAGE_BYTES + (size_t)r * 128;
-                uint8_t* xs = xb + CHUNK_BYTES;
+                if (turn == grp) {
+                    mbar_wait(full + st, ph);
+                    uint8_t* xb = st_s + (size_t)st * STAGE_BYTES + (size_t)r * 128;
+                    uint8_t* xs = xb + CHUNK_BYTES;
+                    if (!(p.exp & 1)) {
+                    float4 x[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int pj = (i + r) & 7;            // physical 16-byte slot (rotated: conflict-free)
-                    const int lj = pj ^ (r & 7);           // logical slot under the 128-byte swizzle
-                    float4 x = *reinterpret_cast<float4*>(xb + pj * 16);
-                    const float4 iv = *reinterpret_cast<const float4*>(iv_s + ch * KC + lj * 4);
-                    rowsq = fmaf(x.x * x.x, iv.x, rowsq);
-                    rowsq = fmaf(x.y * x.y, iv.y, rowsq);
-                    rowsq = fmaf(x.z * x.z, iv.z, rowsq);
-                    rowsq = fmaf(x.w * x.w, iv.w, rowsq);
-                    float4 big, sml;
-                    big.x = __uint_as_float(__float_as_uint(x.x) & TF32_MASK);
-                    big.y = __uint_as_float(__float_as_uint(x.y) & TF32_MASK);
-                    big.z = __uint_as_float(__float_as_uint(x.z) & TF32_MASK);
-                    big.w = __uint_as_float(__float_as_uint(x.w) & TF32_MASK);
-                    sml.x = x.x - big.x;
-                    sml.y = x.y - big.y;
-                    sml.z = x.z - big.z;
-                    sml.w = x.w - big.w;
-                    *reinterpret_cast<float4*>(xb + pj * 16) = big;
-                    *reinterpret_cast<float4*>(xs + pj * 16) = sml;
+                    for (int i = 0; i < 8; ++i) {
+                        const int pj = (i + r) & 7;        // physical 16-byte slot (rotated: conflict-free)
+                        x[i] = *reinterpret_cast<const float4*>(xb + pj * 16);
+                    }
+                    float q0 = 0.0f, q1 = 0.0f;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int lj = ((i + r) & 7) ^ (r & 7);  // logical slot under the 128-byte swizzle
+                        const float4 iv = *reinterpret_cast<const float4*>(iv_s + ch * KC + lj * 4);
+                        q0 = fmaf(x[i].x * x[i].x, iv.x, q0);
+                        q1 = fmaf(x[i].y * x[i].y, iv.y, q1);
+                        q0 = fmaf(x[i].z * x[i].z, iv.z, q0);
+                        q1 = fmaf(x[i].w * x[i].w, iv.w, q1);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int pj = (i + r) & 7;
+                        float4 big, sml;
+                        big.x = __uint_as_float(__float_as_uint(x[i].x) & TF32_MASK);
+                        big.y = __uint_as_float(__float_as_uint(x[i].y) & TF32_MASK);
+                        big.z = __uint_as_float(__float_as_uint(x[i].z) & TF32_MASK);
+                        big.w = __uint_as_float(__float_as_uint(x[i].w) & TF32_MASK);
+                        sml.x = x[i].x - big.x;
+                        sml.y = x[i].y - big.y;
+                        sml.z = x[i].z - big.z;
+                        sml.w = x[i].w - big.w;
+                        *reinterpret_cast<float4*>(xb + pj * 16) = big;
+                        *reinterpret_cast<float4*>(xs + pj * 16) = sml;
+                    }
+                    rowsq += q0 + q1;
+                    }
+                    fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
+                    mbar_arrive(conv + st);
                 }
-                fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
-                mbar_arrive(conv + st);
+                if (++turn == p.cgroups) turn = 0;
                 if (++st == p.nstage) {
                     st = 0;
                     ph ^= 1;
                 }
             }
-            // the row terms of this tile go to the epilogue warps (slot = accumulator parity)
+            // this group's part of the tile's row terms goes to the epilogue warps (slot = accumulator parity)
             mbar_wait(rempty + acc, accph ^ 1);
-            rowsq_s[acc * TILE_M + r] = rowsq;
+            rowsq_s[(acc * p.cgroups + grp) * TILE_M + r] = rowsq;
             mbar_arrive(rfull + acc);
             if (++acc == 2) {
                 acc = 0;
@@ -322,33 +342,49 @@ emission_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
         int acc = 0;
         uint32_t accph = 0;
 
-        auto epilogue = [&](int tile, bool active, float rowsq, int a, uint32_t aph) {
-            const long long row = (long long)tile * TILE_M + r;
-            const bool in_range = row < total_rows;
-            int b = 0, t = 0;
-            bool live = false;
-            if (in_range) {
-                b = (int)(row / p.Tmax);
-                t = (int)(row - (long long)b * p.Tmax);
-                live = t < p.lengths[b];
+        // Rows behind the last live tile of their video are zero-filled here (the interface promises em = 0,
+        // rowterm = 0 for t >= length), in blocks of 128 flattened rows dealt round-robin; this runs while the
+        // ring fills, before the first accumulator is ready.
+        {
+            const long long nblk = (total_rows + TILE_M - 1) / TILE_M;
+            for (long long fb = blockIdx.x; fb < nblk; fb += gridDim.x) {
+                const long long row = fb * TILE_M + r;
+                if (row >= total_rows) continue;
+                const int b = (int)(row / p.Tmax);
+                const int t = (int)(row - (long long)b * p.Tmax);
+                const int len = max(p.lengths[b], 0);
+                if (t < (len + TILE_M - 1) / TILE_M * TILE_M) continue;
+                float* em_r = p.em + (size_t)row * p.ldc;
+                for (int c4 = 0; c4 * 4 < p.ldc; ++c4) *reinterpret_cast<float4*>(em_r + c4 * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+                p.rowterm[row] = 0.0f;
             }
+        }
+
+        for (int g = blockIdx.x; cur.locate(g, p.lengths, p.B, TILE_M, vb, vj, vlen); g += gridDim.x) {
+            mbar_wait(rfull + acc, accph);
+            float rowsq = 0.0f;
+            for (int gq = 0; gq < p.cgroups; ++gq) rowsq += rowsq_s[(acc * p.cgroups + gq) * TILE_M + r];
+            mbar_arrive(rempty + acc);
+
+            const int t = vj * TILE_M + r;
+            const bool in_range = t < p.Tmax;   // rows past Tmax belong to the next video: scored, not stored
+            const bool live = t < vlen;
+            const long long row = (long long)vb * p.Tmax + t;
             float v[NPAD];
-            if (active) {
-                mbar_wait(tfull + a, aph);
-                tc_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + a * ACC_STRIDE;
+            mbar_wait(tfull + acc, accph);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * ACC_STRIDE;
 #pragma unroll
-                for (int i = 0; i < NB; ++i) tc_ld16(taddr + 16 * i, v + 16 * i);
-                tc_wait_ld();
-                tc_fence_before();
-                mbar_arrive(tempty + a);
-            }
+            for (int i = 0; i < NB; ++i) tc_ld16(taddr + 16 * i, v + 16 * i);
+            tc_wait_ld();
+            tc_fence_before();
+            mbar_arrive(tempty + acc);
+
             double contrib = 0.0;
             if (in_range) {
                 float* em_r = p.em + (size_t)row * p.ldc;
                 float rt = 0.0f;
                 if (live) {
-                    // live implies active: the accumulators are valid
                     const float* pen_r = p.penalty ? p.penalty + (size_t)row * p.C : nullptr;
                     float m = NEG;
 #pragma unroll
@@ -376,37 +412,22 @@ emission_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
                 }
 #pragma unroll
                 for (int c4 = 0; c4 < NPAD / 4; ++c4)
-                    if (c4 * 4 < p.ldc)
+                    if (c4 * 4 < p.ldc && !(p.exp & 4))
                         *reinterpret_cast<float4*>(em_r + c4 * 4) = make_float4(v[c4 * 4], v[c4 * 4 + 1], v[c4 * 4 + 2], v[c4 * 4 + 3]);
                 p.rowterm[row] = rt;
             }
-            // per-video offset: one f64 atomic per warp when the warp sits inside one video
-            const int b0 = __shfl_sync(FULL, b, 0);
-            const bool same = __all_sync(FULL, !in_range || b == b0);
-            if (same) {
-                contrib = warp_sum(contrib);
-                if (lane == 0 && contrib != 0.0) atomicAdd(p.offset + b0, contrib);
-            } else if (live) {
-                atomicAdd(p.offset + b, contrib);
-            }
-        };
+            // per-video offset: the tile lies inside one video, one f64 atomic per warp
+            contrib = warp_sum(contrib);
+            if (lane == 0 && contrib != 0.0) atomicAdd(p.offset + vb, contrib);
 
-        for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-            const bool active = tile_active(p, tile);
-            float rowsq = 0.0f;
-            if (active) {
-                mbar_wait(rfull + acc, accph);
-                rowsq = rowsq_s[acc * TILE_M + r];
-                mbar_arrive(rempty + acc);
-            }
-            epilogue(tile, active, rowsq, acc, accph);
-            if (active && ++acc == 2) {
+            if (++acc == 2) {
                 acc = 0;
                 accph ^= 1;
             }
         }
     }
 
+done:
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
@@ -457,7 +478,7 @@ static bool make_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t
 }
 
 struct Plan {
-    int npad, nchunk, nstage;
+    int npad, nchunk, nstage, cgroups;
     size_t smem;
 };
 
@@ -465,10 +486,14 @@ static bool plan(int D, int C, Plan* pl) {
     if (C > 64 || D % 4 != 0 || D < 4) return false;
     pl->npad = (C + 15) / 16 * 16;
     pl->nchunk = (D + KC - 1) / KC;
-    const size_t fixed = (size_t)pl->nchunk * 2 * pl->npad * 128 + (size_t)(pl->npad + pl->nchunk * KC) * 4 +
-                         (3 * MAX_STAGES + 9) * 8 + 16 + 2 * TILE_M * 4;
     const size_t cap = 227 * 1024;
-    if (fixed + 2 * (size_t)STAGE_BYTES > cap) return false;
+    size_t fixed = 0;
+    for (pl->cgroups = CONV_GROUPS; pl->cgroups >= 1; --pl->cgroups) {
+        fixed = (size_t)pl->nchunk * 2 * pl->npad * 128 + (size_t)(pl->npad + pl->nchunk * KC) * 4 + (3 * MAX_STAGES + 9) * 8 + 16 +
+                2 * (size_t)pl->cgroups * TILE_M * 4;
+        if (fixed + 2 * (size_t)STAGE_BYTES <= cap) break;
+    }
+    if (pl->cgroups < 1) return false;
     int ns = (int)((cap - fixed) / STAGE_BYTES);
     if (ns > MAX_STAGES) ns = MAX_STAGES;
     pl->nstage = ns;
@@ -513,9 +538,23 @@ int launch_emission_tc(const float* X, const float* w, const float* bias, const 
     Params p;
     p.bias = bias; p.inv_var = inv_var; p.penalty = penalty; p.lengths = lengths; p.em = em; p.rowterm = rowterm;
     p.offset = offset; p.row_const = row_const; p.B = B; p.Tmax = Tmax; p.D = D; p.C = C; p.ldc = ldc;
-    p.npad = pl.npad; p.nchunk = pl.nchunk; p.nstage = pl.nstage;
-    p.ntiles = (int)((rows + TILE_M - 1) / TILE_M);
-    int grid = num_sms < p.ntiles ? num_sms : p.ntiles;
+    p.npad = pl.npad; p.nchunk = pl.nchunk; p.nstage = pl.nstage; p.cgroups = pl.cgroups;
+    {
+        static int ex = -1;
+        if (ex < 0) {
+            const char* e = getenv("HSMM_ETC_EXP");
+            ex = e ? atoi(e) : 0;
+        }
+        p.exp = ex;
+        static int nst = -1;
+        if (nst < 0) {
+            const char* e = getenv("HSMM_ETC_NSTAGE");
+            nst = e ? atoi(e) : 0;
+        }
+        if (nst >= 2 && nst < p.nstage) p.nstage = nst;
+    }
+    const long long max_tiles = (long long)B * ((Tmax + TILE_M - 1) / TILE_M);
+    int grid = num_sms < max_tiles ? num_sms : (int)max_tiles;
     if (grid < 1) grid = 1;
 
 #define HSMM_ETC_LAUNCH(NB)                                                                                          \
