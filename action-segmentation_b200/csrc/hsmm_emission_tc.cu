@@ -27,91 +27,23 @@
 
 #include <cstdlib>
 
-#include "hsmm_common.cuh"
+#include "hsmm_tc.cuh"
 
 namespace hsmm {
 
 namespace etc {
 
+using namespace tc;
+
 constexpr int TILE_M = 128;       // frames per tile = UMMA M
 constexpr int KC = 32;            // floats per chunk = one 128-byte swizzle row
 constexpr int CHUNK_BYTES = TILE_M * KC * 4;  // 16 KB
 constexpr int STAGE_BYTES = 2 * CHUNK_BYTES;  // big + small
-constexpr int CONV_GROUPS = 2;   // converter groups (4 warps each) compiled in; Params::cgroups of them take alternate chunks
+constexpr int CONV_GROUPS = 1;   // converter groups (4 warps each) compiled in; Params::cgroups of them take alternate chunks
 constexpr int THREADS = 64 + 128 * CONV_GROUPS + 128;
 constexpr int ACC_STRIDE = 64;    // TMEM columns between the two accumulators
 constexpr int TMEM_COLS = 128;
 constexpr int MAX_STAGES = 6;
-constexpr uint32_t TF32_MASK = 0xffffe000u;
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra WAIT_DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "WAIT_DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-            smem_u32(dst)),
-        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-        : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(d_tmem),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
-        : "memory");
-}
-// 16 consecutive accumulator columns of this thread's TMEM lane
-__device__ __forceinline__ void tc_ld16(uint32_t taddr, float* v) {
-    uint32_t r[16];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr)
-        : "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major, 128-byte swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
-// start address >> 4 in [0,14), LBO (unused for swizzled K-major) = 1 in [16,30), SBO = 1024 B (8 rows of
-// 128 B) >> 4 in [32,46), version = 1 in [46,48), layout SWIZZLE_128B = 2 in [61,64).
-__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
-    return (uint64_t)((saddr & 0x3ffffu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
-           ((uint64_t)2 << 61);
-}
 
 struct Params {
     const float* bias;
@@ -131,7 +63,9 @@ struct Params {
 };
 
 template <int NB>  // NPAD = 16 * NB
-__global__ void __launch_bounds__(THREADS, 1)
+// (THREADS, 2): caps the kernel at 96 registers -- 30 K registers per CTA, so that two CTAs of the DP kernels (12-16 K
+// registers each) stay resident beside it and use the issue slots this HBM-bound kernel leaves idle
+__global__ void __launch_bounds__(THREADS, 2)
 emission_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w, const Params p) {
     constexpr int NPAD = 16 * NB;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -447,36 +381,6 @@ __global__ void emission_split_w_kernel(const float* __restrict__ w, int C, int 
     }
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_fn() {
-    static EncodeTiledFn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
-        void* ptr = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
-            qres == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(ptr);
-    }
-    return fn;
-}
-
-static bool make_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
-    EncodeTiledFn fn = encode_fn();
-    if (!fn) return false;
-    cuuint64_t gdim[2] = {cols, rows};
-    cuuint64_t gstr[1] = {cols * sizeof(float)};
-    cuuint32_t box[2] = {(cuuint32_t)KC, box_rows};
-    cuuint32_t estr[2] = {1, 1};
-    return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstr, box, estr,
-              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
 struct Plan {
     int npad, nchunk, nstage, cgroups;
     size_t smem;
@@ -523,8 +427,8 @@ int launch_emission_tc(const float* X, const float* w, const float* bias, const 
     if (rows >= (1ll << 31) - TILE_M) return 1;
     const int dpad = pl.nchunk * KC;
     CUtensorMap mx, mw;
-    if (!make_map(&mx, X, (uint64_t)rows, (uint64_t)D, TILE_M)) return 1;
-    if (!make_map(&mw, workspace, (uint64_t)(2 * pl.npad), (uint64_t)dpad, (uint32_t)pl.npad)) return 1;
+    if (!make_map(&mx, X, (uint64_t)rows, (uint64_t)D, (uint64_t)D, KC, TILE_M)) return 1;
+    if (!make_map(&mw, workspace, (uint64_t)(2 * pl.npad), (uint64_t)dpad, (uint64_t)dpad, KC, (uint32_t)pl.npad)) return 1;
 
     cudaError_t e = cudaMemsetAsync(offset, 0, sizeof(double) * B, st);
     if (e != cudaSuccess) {

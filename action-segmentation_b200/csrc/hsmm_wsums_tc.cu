@@ -1,0 +1,296 @@
+// Class-weighted feature sums on the 5th-generation tensor cores (sm_100a):
+//
+//   out_wx[c][d] += sum_f wgt[f][c] * x[f][d],   out_wsum[c] += sum_f wgt[f][c]      (frames f of all videos)
+//
+// the reduction behind d/d gaussian_means (loss.backward() through the emission scores, semimarkov.py:284-286) and the
+// supervised class means (semimarkov_utils.py:74-126).  It is a (D x F).(F x C) contraction whose reduction dimension
+// is the FRAME index, so both operands are "MN-major" for the tensor core: a frame is one 128-byte row of 32
+// consecutive feature dims (A = X^T, M = feature dim) or of the <= 32 class weights (B = W^T, N = class).  That is
+// the shared-memory image of the emission kernel's TMA boxes, in the one swizzle MN-major tf32 operands may use
+// (128-byte rows, 32-byte pieces permuted by row & 3: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B <-> UMMA SWIZZLE_128B_BASE32B).
+// The SIMT kernel (hsmm_aux.cu) spends 194 warp instructions per frame on this; here the FMAs run on the tensor
+// pipe and the SM only splits the operands (3xTF32: x = xb + xs, w = wb + ws; xb.wb + xs.wb + xb.ws in fp32, the
+// dropped term is ~2^-22 relative).
+//
+// Persistent CTAs (one per SM); a tile is 32 consecutive frames of ONE video, live tiles only, dealt round-robin
+// (TileCursor).  One ring stage = one tile:
+//   warp 0      TMA producer: <= 7 boxes of 32 frames x 32 dims of X and one box of 32 frames x 32 weights
+//   warp 1      MMA issuer (one lane): per 8 frames and per half of the feature dims (M = 128) three
+//               tcgen05.mma.kind::tf32 with N = 32 classes; the two accumulators (128 lanes x 32 columns each) stay
+//               in TMEM for the whole kernel
+//   warps 2..9  converters: in-place split into big/small, rows behind the end of the video and class columns
+//               >= C forced to zero; at the end warps 2..5 read the accumulators and flush them with atomics.
+// Feature column 255 of every stage holds the constant 1 (chunk slot 7 is never loaded), so that accumulator row
+// 255 is the column sum of the weights (out_wsum).
+#include "hsmm_tc.cuh"
+
+namespace hsmm {
+
+namespace wtc {
+
+using namespace tc;
+
+constexpr int TF = 32;                       // frames per tile
+constexpr int KC = 32;                       // floats per 128-byte row
+constexpr int NCH = 8;                       // chunk slots per stage (256 feature columns)
+constexpr int CHUNK_BYTES = TF * 128;        // 4 KB: one chunk of one tile
+constexpr int XPART = NCH * CHUNK_BYTES;     // 32 KB
+constexpr int WPART = TF * 128;              // 4 KB
+constexpr int STAGE_BYTES = 2 * XPART + 2 * WPART;  // big + small of X and of the weights: 72 KB
+constexpr int NSTAGE = 3;
+constexpr int CONV_THREADS = 256;
+constexpr int THREADS = 64 + CONV_THREADS;
+constexpr int TMEM_COLS = 64;
+constexpr int NPAD = 32;                     // classes per accumulator (UMMA N)
+constexpr size_t SMEM_BYTES = (size_t)NSTAGE * STAGE_BYTES + 128;
+
+struct Params {
+    const int32_t* lengths;
+    float* out_wx;
+    float* out_wsum;
+    int B, Tmax, D, C;
+    int nchunk;  // ceil(D / 32) <= 7
+};
+
+// (THREADS, 2): <= 96 registers, 30 K per CTA: two DP CTAs stay resident beside this HBM-bound kernel
+__global__ void __launch_bounds__(THREADS, 2)
+weighted_sums_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w, const Params p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    if (smem_u32(smem_raw) & 1023u) __trap();
+    uint8_t* st_s = smem_raw;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(st_s + (size_t)NSTAGE * STAGE_BYTES);
+    uint64_t* full = bars;             // TMA -> converters
+    uint64_t* conv = full + NSTAGE;    // converters -> MMA
+    uint64_t* empty = conv + NSTAGE;   // MMA -> TMA
+    uint64_t* done = empty + NSTAGE;   // last MMA -> epilogue
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NSTAGE; ++s) {
+            mbar_init(full + s, 1);
+            mbar_init(conv + s, CONV_THREADS);
+            mbar_init(empty + s, 1);
+        }
+        mbar_init(done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // the ring starts as zeros (chunk slots that are never loaded stay zero) except the ones column: feature 255 =
+    // element 3 of the logical 16-byte unit 7 of every frame row of chunk slot 7 (32-byte piece 3 ^ (row & 3), upper half)
+    for (int i = threadIdx.x; i < NSTAGE * STAGE_BYTES / 16; i += THREADS)
+        reinterpret_cast<float4*>(st_s)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();
+    if (threadIdx.x < NSTAGE * TF) {
+        const int s = threadIdx.x / TF, f = threadIdx.x % TF;
+        float* rowp = reinterpret_cast<float*>(st_s + (size_t)s * STAGE_BYTES + 7 * CHUNK_BYTES + f * 128 + ((((3 ^ (f & 3)) << 1) | 1) * 16));
+        rowp[3] = 1.0f;
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    TileCursor cur;
+    int vb, vj, vlen;
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        int st = 0;
+        uint32_t ph = 0;
+        for (int g = blockIdx.x; cur.locate(g, p.lengths, p.B, TF, vb, vj, vlen); g += gridDim.x) {
+            if (lane == 0) {
+                const int row0 = vb * p.Tmax + vj * TF;
+                uint8_t* sb = st_s + (size_t)st * STAGE_BYTES;
+                mbar_wait(empty + st, ph ^ 1);
+                mbar_arrive_expect_tx(full + st, (uint32_t)(p.nchunk * CHUNK_BYTES + WPART));
+                for (int ch = 0; ch < p.nchunk; ++ch) tma_load_2d(sb + ch * CHUNK_BYTES, &tmap_x, full + st, ch * KC, row0);
+                tma_load_2d(sb + 2 * XPART, &tmap_w, full + st, 0, row0);
+                if (++st == NSTAGE) {
+                    st = 0;
+                    ph ^= 1;
+                }
+            }
+            st = __shfl_sync(FULL, st, 0);
+            ph = __shfl_sync(FULL, ph, 0);
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        // D (f32), A = B = tf32, both MN-major, N = 32, M = 128
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(NPAD >> 3) << 17) |
+                               ((uint32_t)(128 >> 4) << 24);
+        int st = 0;
+        uint32_t ph = 0;
+        uint32_t accum = 0;
+        for (int g = blockIdx.x; cur.locate(g, p.lengths, p.B, TF, vb, vj, vlen); g += gridDim.x) {
+            if (lane == 0) {
+                mbar_wait(conv + st, ph);
+                tc_fence_after();
+                const uint32_t xb0 = smem_u32(st_s + (size_t)st * STAGE_BYTES);
+                const uint32_t wb0 = xb0 + 2 * XPART;
+#pragma unroll
+                for (int ks = 0; ks < TF / 8; ++ks) {
+                    const uint64_t wb = smem_desc_sw128b32_mn(wb0 + ks * 1024, 1024, 512);
+                    const uint64_t ws = smem_desc_sw128b32_mn(wb0 + WPART + ks * 1024, 1024, 512);
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        const uint32_t xa = xb0 + half * 4 * CHUNK_BYTES + ks * 1024;
+                        const uint64_t xb = smem_desc_sw128b32_mn(xa, CHUNK_BYTES, 512);
+                        const uint64_t xs = smem_desc_sw128b32_mn(xa + XPART, CHUNK_BYTES, 512);
+                        const uint32_t d_tmem = tmem_base + half * NPAD;
+                        tc_mma_tf32(d_tmem, xs, wb, idesc, accum);
+                        tc_mma_tf32(d_tmem, xb, ws, idesc, 1);
+                        tc_mma_tf32(d_tmem, xb, wb, idesc, 1);
+                    }
+                    accum = 1;
+                }
+                tc_commit(empty + st);
+                if (++st == NSTAGE) {
+                    st = 0;
+                    ph ^= 1;
+                }
+            }
+            st = __shfl_sync(FULL, st, 0);
+            ph = __shfl_sync(FULL, ph, 0);
+            accum = __shfl_sync(FULL, accum, 0);
+        }
+        if (lane == 0) tc_commit(done);
+        __syncwarp();
+    } else {
+        // ===================== converters =====================
+        const int tc_id = threadIdx.x - 64;   // 0..255
+        int st = 0;
+        uint32_t ph = 0;
+        bool any = false;
+        for (int g = blockIdx.x; cur.locate(g, p.lengths, p.B, TF, vb, vj, vlen); g += gridDim.x) {
+            any = true;
+            const int nf = min(TF, vlen - vj * TF);   // live frames of the tile
+            uint8_t* sb = st_s + (size_t)st * STAGE_BYTES;
+            mbar_wait(full + st, ph);
+            // X: 16-byte unit u of the stage <-> (chunk u >> 8, frame row (u >> 3) & 31); elementwise, in place
+            float4 x[NCH - 1];
+#pragma unroll
+            for (int i = 0; i < NCH - 1; ++i) {
+                const int u = tc_id + i * CONV_THREADS;
+                x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (i < p.nchunk) x[i] = *reinterpret_cast<const float4*>(sb + (size_t)u * 16);
+            }
+            // weights: unit <-> (frame row tc_id >> 3, physical 16-byte slot tc_id & 7)
+            const int wf = tc_id >> 3;
+            const int wpj = tc_id & 7;                       // physical 16-byte slot; its 32-byte piece is permuted by (row & 3)
+            const int wc0 = (((((wpj >> 1) ^ (wf & 3)) << 1) | (wpj & 1))) * 4;   // first class of the unit
+            float4 w = *reinterpret_cast<const float4*>(sb + 2 * XPART + (size_t)tc_id * 16);
+            const int xf = (tc_id >> 3) & 31;               // frame row of this thread's X units (the same for every chunk)
+            const bool xlive = xf < nf;
+#pragma unroll
+            for (int i = 0; i < NCH - 1; ++i) {
+                if (i < p.nchunk) {
+                    const int u = tc_id + i * CONV_THREADS;
+                    float4 v = x[i];
+                    if (!xlive) v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    float4 big, sml;
+                    big.x = __uint_as_float(__float_as_uint(v.x) & TF32_MASK);
+                    big.y = __uint_as_float(__float_as_uint(v.y) & TF32_MASK);
+                    big.z = __uint_as_float(__float_as_uint(v.z) & TF32_MASK);
+                    big.w = __uint_as_float(__float_as_uint(v.w) & TF32_MASK);
+                    sml.x = v.x - big.x;
+                    sml.y = v.y - big.y;
+                    sml.z = v.z - big.z;
+                    sml.w = v.w - big.w;
+                    *reinterpret_cast<float4*>(sb + (size_t)u * 16) = big;
+                    *reinterpret_cast<float4*>(sb + XPART + (size_t)u * 16) = sml;
+                }
+            }
+            {
+                if (wf >= nf) w = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (wc0 + 0 >= p.C) w.x = 0.f;
+                if (wc0 + 1 >= p.C) w.y = 0.f;
+                if (wc0 + 2 >= p.C) w.z = 0.f;
+                if (wc0 + 3 >= p.C) w.w = 0.f;
+                float4 big, sml;
+                big.x = __uint_as_float(__float_as_uint(w.x) & TF32_MASK);
+                big.y = __uint_as_float(__float_as_uint(w.y) & TF32_MASK);
+                big.z = __uint_as_float(__float_as_uint(w.z) & TF32_MASK);
+                big.w = __uint_as_float(__float_as_uint(w.w) & TF32_MASK);
+                sml.x = w.x - big.x;
+                sml.y = w.y - big.y;
+                sml.z = w.z - big.z;
+                sml.w = w.w - big.w;
+                *reinterpret_cast<float4*>(sb + 2 * XPART + (size_t)tc_id * 16) = big;
+                *reinterpret_cast<float4*>(sb + 2 * XPART + WPART + (size_t)tc_id * 16) = sml;
+            }
+            fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
+            mbar_arrive(conv + st);
+            if (++st == NSTAGE) {
+                st = 0;
+                ph ^= 1;
+            }
+        }
+        // ===================== final flush (warps 2..5: TMEM lane quarter = warp % 4) =====================
+        if (warp < 6 && any) {
+            mbar_wait(done, 0);
+            tc_fence_after();
+            const int q = warp & 3;
+            const int r = q * 32 + lane;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                float v[NPAD];
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + half * NPAD;
+                tc_ld16(taddr, v);
+                tc_ld16(taddr + 16, v + 16);
+                tc_wait_ld();
+                const int d = half * 128 + r;
+#pragma unroll
+                for (int c = 0; c < NPAD; ++c) {
+                    if (c < p.C) {
+                        if (d < p.D) atomicAdd(p.out_wx + (size_t)c * p.D + d, v[c]);
+                        if (d == 255) atomicAdd(p.out_wsum + c, v[c]);
+                    }
+                }
+            }
+            tc_fence_before();
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+}  // namespace wtc
+
+// returns 1 when the shape / alignment is not eligible (caller falls back to the SIMT kernel), 0 on launch, < 0 on error
+int launch_weighted_sums_tc(const float* X, const float* wgt, int ldc, const int32_t* lengths, int B, int Tmax, int D, int C,
+                            float* out_wx, float* out_wsum, int num_sms, cudaStream_t st) {
+    using namespace wtc;
+    if (D % 4 != 0 || D < 4 || D > 7 * KC || C < 1 || C > NPAD || ldc % 4 != 0 || ldc > NPAD) return 1;
+    if ((reinterpret_cast<uintptr_t>(X) & 15) || (reinterpret_cast<uintptr_t>(wgt) & 15)) return 1;
+    const long long rows = (long long)B * Tmax;
+    if (rows < 1 || rows >= (1ll << 31) - TF) return 1;
+    CUtensorMap mx, mw;
+    if (!tc::make_map(&mx, X, (uint64_t)rows, (uint64_t)D, (uint64_t)D, KC, TF, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return 1;
+    if (!tc::make_map(&mw, wgt, (uint64_t)rows, (uint64_t)ldc, (uint64_t)ldc, KC, TF, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return 1;
+
+    Params p;
+    p.lengths = lengths; p.out_wx = out_wx; p.out_wsum = out_wsum; p.B = B; p.Tmax = Tmax; p.D = D; p.C = C;
+    p.nchunk = (D + KC - 1) / KC;
+    const long long max_tiles = (long long)B * ((Tmax + TF - 1) / TF);
+    int grid = num_sms < max_tiles ? num_sms : (int)max_tiles;
+    if (grid < 1) grid = 1;
+    cudaError_t e = cudaFuncSetAttribute(weighted_sums_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    if (e != cudaSuccess) {
+        set_error("weighted_sums_tc smem attr: %s", cudaGetErrorString(e));
+        return -3;
+    }
+    weighted_sums_tc_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(mx, mw, p);
+    return check_launch("weighted_sums_tc_kernel");
+}
+
+}  // namespace hsmm
