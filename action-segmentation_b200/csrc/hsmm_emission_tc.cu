@@ -152,51 +152,52 @@ emission_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
             ph = __shfl_sync(FULL, ph, 0);
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
+        // ===================== MMA issuer (whole warp converged, one elected lane issues) =====================
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NPAD >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
-        if (lane == 0) mbar_wait(wbar, 0);
-        __syncwarp();
+        const uint32_t leader = elect_one();
+        const int total_tiles = count_tiles(p.lengths, p.B, TILE_M);
+        const int my_tiles = (total_tiles > (int)blockIdx.x) ? (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+        mbar_wait(wbar, 0);
+        const uint64_t desc0 = smem_desc_sw128(0);   // descriptor of shared address 0: the address field is added per MMA
+        const uint32_t st0 = smem_u32(st_s), w0 = smem_u32(w_s);
         int st = 0;
         uint32_t ph = 0;
         int acc = 0;
         uint32_t accph = 0;
-        for (int g = blockIdx.x; cur.locate(g, p.lengths, p.B, TILE_M, vb, vj, vlen); g += gridDim.x) {
-            if (lane == 0) {
-                mbar_wait(tempty + acc, accph ^ 1);
+        for (int it = 0; it < my_tiles; ++it) {
+            mbar_wait(tempty + acc, accph ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * ACC_STRIDE;
+            uint32_t accum = 0;
+            for (int ch = 0; ch < p.nchunk; ++ch) {
+                mbar_wait(conv + st, ph);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * ACC_STRIDE;
-                uint32_t accum = 0;
-                for (int ch = 0; ch < p.nchunk; ++ch) {
-                    mbar_wait(conv + st, ph);
-                    tc_fence_after();
-                    const uint32_t xb = smem_u32(st_s + (size_t)st * STAGE_BYTES);
-                    const uint32_t xs = xb + CHUNK_BYTES;
-                    const uint32_t wb = smem_u32(w_s + (size_t)ch * w_chunk_bytes);
-                    const uint32_t ws = wb + NPAD * 128;
-                    const int ksteps = (ch == p.nchunk - 1) ? klast : 4;
-                    for (int ks = 0; ks < ksteps && !(p.exp & 2); ++ks) {
+                const uint64_t xb = desc_at(desc0, st0 + st * STAGE_BYTES);
+                const uint64_t xs = desc_at(xb, CHUNK_BYTES);
+                const uint64_t wb = desc_at(desc0, w0 + ch * w_chunk_bytes);
+                const uint64_t ws = desc_at(wb, NPAD * 128);
+                const int ksteps = (ch == p.nchunk - 1) ? klast : 4;
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    if (ks < ksteps && !(p.exp & 2)) {
                         const uint32_t ko = ks * 32;  // 8 tf32 = 32 bytes inside the 128-byte swizzle row
-                        tc_mma_tf32(d_tmem, smem_desc_sw128(xs + ko), smem_desc_sw128(wb + ko), idesc, accum);
+                        tc_mma_tf32_lead(d_tmem, desc_at(xs, ko), desc_at(wb, ko), idesc, accum, leader);
                         accum = 1;
-                        tc_mma_tf32(d_tmem, smem_desc_sw128(xb + ko), smem_desc_sw128(ws + ko), idesc, 1);
-                        tc_mma_tf32(d_tmem, smem_desc_sw128(xb + ko), smem_desc_sw128(wb + ko), idesc, 1);
-                    }
-                    tc_commit(empty + st);  // the stage may be refilled once these MMAs have read it
-                    if (++st == p.nstage) {
-                        st = 0;
-                        ph ^= 1;
+                        tc_mma_tf32_lead(d_tmem, desc_at(xb, ko), desc_at(ws, ko), idesc, 1, leader);
+                        tc_mma_tf32_lead(d_tmem, desc_at(xb, ko), desc_at(wb, ko), idesc, 1, leader);
                     }
                 }
-                tc_commit(tfull + acc);
-                if (++acc == 2) {
-                    acc = 0;
-                    accph ^= 1;
+                tc_commit_lead(empty + st, leader);  // the stage may be refilled once these MMAs have read it
+                if (++st == p.nstage) {
+                    st = 0;
+                    ph ^= 1;
                 }
             }
-            st = __shfl_sync(FULL, st, 0);
-            ph = __shfl_sync(FULL, ph, 0);
-            acc = __shfl_sync(FULL, acc, 0);
-            accph = __shfl_sync(FULL, accph, 0);
+            tc_commit_lead(tfull + acc, leader);
+            if (++acc == 2) {
+                acc = 0;
+                accph ^= 1;
+            }
         }
     } else if (warp < 2 + 4 * CONV_GROUPS) {
         // ===================== converters (CONV_GROUPS x 128 threads, thread <-> frame) =====================

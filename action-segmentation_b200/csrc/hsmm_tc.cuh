@@ -88,6 +88,59 @@ __device__ __forceinline__ uint64_t smem_desc_sw128b32_mn(uint32_t saddr, uint32
            ((uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32) | ((uint64_t)1 << 46) | ((uint64_t)1 << 61);
 }
 
+
+// ---- issue helpers for a CONVERGED warp ---------------------------------------------------------------------------
+// The MMA-issuing warp runs its whole loop with all 32 lanes converged and warp-uniform operands; only the tcgen05
+// instruction itself is predicated on the elected lane.  Behind an `if (lane == 0)` branch the compiler has to move
+// every descriptor from vector to uniform registers (ELECT + R2UR per operand): ~37 SASS instructions per MMA, which
+// made the single issuing thread the bottleneck of the emission kernel (1500 cycles per 16 KB chunk).
+__device__ __forceinline__ uint32_t elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred q;\n"
+        "elect.sync _|q, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, q;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred;
+}
+__device__ __forceinline__ void tc_mma_tf32_lead(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum,
+                                                 uint32_t leader) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p, q;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "setp.ne.b32 q, %5, 0;\n"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum), "r"(leader)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit_lead(uint64_t* bar, uint32_t leader) {
+    asm volatile(
+        "{\n"
+        ".reg .pred q;\n"
+        "setp.ne.b32 q, %1, 0;\n"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(leader)
+        : "memory");
+}
+// descriptor with a new start address: only the low 14-bit address field changes
+__device__ __forceinline__ uint64_t desc_at(uint64_t desc0, uint32_t byte_offset) { return desc0 + (uint64_t)(byte_offset >> 4); }
+
+// number of live tiles of the batch (warp-cooperative, the result is warp-uniform): sum_b ceil(len_b / TF)
+__device__ __forceinline__ int count_tiles(const int32_t* __restrict__ lengths, int B, int TF) {
+    int total = 0;
+    for (int b0 = 0; b0 < B; b0 += 32) {
+        const int b = b0 + (int)(threadIdx.x & 31);
+        const int len = (b < B) ? max(lengths[b], 0) : 0;
+        total += __reduce_add_sync(FULL, (len + TF - 1) / TF);
+    }
+    return total;
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);

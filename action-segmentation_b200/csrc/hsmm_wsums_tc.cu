@@ -120,47 +120,46 @@ weighted_sums_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
             ph = __shfl_sync(FULL, ph, 0);
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
+        // ===================== MMA issuer (whole warp converged, one elected lane issues) =====================
         // D (f32), A = B = tf32, both MN-major, N = 32, M = 128
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(NPAD >> 3) << 17) |
                                ((uint32_t)(128 >> 4) << 24);
+        const uint32_t leader = elect_one();
+        const int total_tiles = count_tiles(p.lengths, p.B, TF);
+        const int my_tiles = (total_tiles > (int)blockIdx.x) ? (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+        const uint64_t xdesc0 = smem_desc_sw128b32_mn(0, CHUNK_BYTES, 512);   // address field added per MMA
+        const uint64_t wdesc0 = smem_desc_sw128b32_mn(0, 1024, 512);
+        const uint32_t st0 = smem_u32(st_s);
         int st = 0;
         uint32_t ph = 0;
         uint32_t accum = 0;
-        for (int g = blockIdx.x; cur.locate(g, p.lengths, p.B, TF, vb, vj, vlen); g += gridDim.x) {
-            if (lane == 0) {
-                mbar_wait(conv + st, ph);
-                tc_fence_after();
-                const uint32_t xb0 = smem_u32(st_s + (size_t)st * STAGE_BYTES);
-                const uint32_t wb0 = xb0 + 2 * XPART;
+        for (int it = 0; it < my_tiles; ++it) {
+            mbar_wait(conv + st, ph);
+            tc_fence_after();
+            const uint32_t xb0 = st0 + st * STAGE_BYTES;
+            const uint32_t wb0 = xb0 + 2 * XPART;
 #pragma unroll
-                for (int ks = 0; ks < TF / 8; ++ks) {
-                    const uint64_t wb = smem_desc_sw128b32_mn(wb0 + ks * 1024, 1024, 512);
-                    const uint64_t ws = smem_desc_sw128b32_mn(wb0 + WPART + ks * 1024, 1024, 512);
+            for (int ks = 0; ks < TF / 8; ++ks) {
+                const uint64_t wb = desc_at(wdesc0, wb0 + ks * 1024);
+                const uint64_t ws = desc_at(wb, WPART);
 #pragma unroll
-                    for (int half = 0; half < 2; ++half) {
-                        const uint32_t xa = xb0 + half * 4 * CHUNK_BYTES + ks * 1024;
-                        const uint64_t xb = smem_desc_sw128b32_mn(xa, CHUNK_BYTES, 512);
-                        const uint64_t xs = smem_desc_sw128b32_mn(xa + XPART, CHUNK_BYTES, 512);
-                        const uint32_t d_tmem = tmem_base + half * NPAD;
-                        tc_mma_tf32(d_tmem, xs, wb, idesc, accum);
-                        tc_mma_tf32(d_tmem, xb, ws, idesc, 1);
-                        tc_mma_tf32(d_tmem, xb, wb, idesc, 1);
-                    }
-                    accum = 1;
+                for (int half = 0; half < 2; ++half) {
+                    const uint64_t xb = desc_at(xdesc0, xb0 + half * 4 * CHUNK_BYTES + ks * 1024);
+                    const uint64_t xs = desc_at(xb, XPART);
+                    const uint32_t d_tmem = tmem_base + half * NPAD;
+                    tc_mma_tf32_lead(d_tmem, xs, wb, idesc, accum, leader);
+                    tc_mma_tf32_lead(d_tmem, xb, ws, idesc, 1, leader);
+                    tc_mma_tf32_lead(d_tmem, xb, wb, idesc, 1, leader);
                 }
-                tc_commit(empty + st);
-                if (++st == NSTAGE) {
-                    st = 0;
-                    ph ^= 1;
-                }
+                accum = 1;
             }
-            st = __shfl_sync(FULL, st, 0);
-            ph = __shfl_sync(FULL, ph, 0);
-            accum = __shfl_sync(FULL, accum, 0);
+            tc_commit_lead(empty + st, leader);
+            if (++st == NSTAGE) {
+                st = 0;
+                ph ^= 1;
+            }
         }
-        if (lane == 0) tc_commit(done);
-        __syncwarp();
+        tc_commit_lead(done, leader);
     } else {
         // ===================== converters =====================
         const int tc_id = threadIdx.x - 64;   // 0..255
