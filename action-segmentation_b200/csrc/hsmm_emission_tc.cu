@@ -41,8 +41,6 @@ constexpr int CHUNK_BYTES = TILE_M * KC * 4;  // 16 KB
 constexpr int STAGE_BYTES = 2 * CHUNK_BYTES;  // big + small
 constexpr int CONV_GROUPS = 1;   // converter groups (4 warps each) compiled in; Params::cgroups of them take alternate chunks
 constexpr int THREADS = 64 + 128 * CONV_GROUPS + 128;
-constexpr int ACC_STRIDE = 64;    // TMEM columns between the two accumulators
-constexpr int TMEM_COLS = 128;
 constexpr int MAX_STAGES = 6;
 
 struct Params {
@@ -68,6 +66,11 @@ template <int NB>  // NPAD = 16 * NB
 __global__ void __launch_bounds__(THREADS, 2)
 emission_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w, const Params p) {
     constexpr int NPAD = 16 * NB;
+    // One accumulator = 2 NPAD TMEM columns: [0, NPAD) collects xb.wb + xs.wb, [NPAD, 2 NPAD) collects xb.ws (the big and
+    // small class weights sit behind each other in shared memory, so xb meets both in ONE MMA with N = 2 NPAD: two MMAs
+    // per k-step instead of three); the epilogue adds the two halves.  Two accumulators (double buffer).
+    constexpr int ACC_STRIDE = 2 * NPAD;
+    constexpr int TMEM_COLS = (4 * NPAD <= 64) ? 64 : (4 * NPAD <= 128 ? 128 : 256);
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // carve: [W: nchunk x (big NPAD x 128 B, small NPAD x 128 B)] [stages] [bias NPAD] [inv_var nchunk*32] [barriers]
     // (offset arithmetic on the __shared__ symbol keeps the address space visible to the compiler: LDS/STS, not generic LD/ST)
@@ -153,7 +156,8 @@ emission_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (whole warp converged, one elected lane issues) =====================
-        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NPAD >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+        const uint32_t idesc_n = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NPAD >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+        const uint32_t idesc_2n = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(2 * NPAD >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
         const uint32_t leader = elect_one();
         const int total_tiles = count_tiles(p.lengths, p.B, TILE_M);
         const int my_tiles = (total_tiles > (int)blockIdx.x) ? (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
@@ -174,17 +178,15 @@ emission_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
                 tc_fence_after();
                 const uint64_t xb = desc_at(desc0, st0 + st * STAGE_BYTES);
                 const uint64_t xs = desc_at(xb, CHUNK_BYTES);
-                const uint64_t wb = desc_at(desc0, w0 + ch * w_chunk_bytes);
-                const uint64_t ws = desc_at(wb, NPAD * 128);
+                const uint64_t wb = desc_at(desc0, w0 + ch * w_chunk_bytes);   // NPAD rows big, then NPAD rows small
                 const int ksteps = (ch == p.nchunk - 1) ? klast : 4;
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) {
                     if (ks < ksteps && !(p.exp & 2)) {
                         const uint32_t ko = ks * 32;  // 8 tf32 = 32 bytes inside the 128-byte swizzle row
-                        tc_mma_tf32_lead(d_tmem, desc_at(xs, ko), desc_at(wb, ko), idesc, accum, leader);
+                        tc_mma_tf32_lead(d_tmem, desc_at(xb, ko), desc_at(wb, ko), idesc_2n, accum, leader);   // xb.[wb; ws]
                         accum = 1;
-                        tc_mma_tf32_lead(d_tmem, desc_at(xb, ko), desc_at(ws, ko), idesc, 1, leader);
-                        tc_mma_tf32_lead(d_tmem, desc_at(xb, ko), desc_at(wb, ko), idesc, 1, leader);
+                        tc_mma_tf32_lead(d_tmem, desc_at(xs, ko), desc_at(wb, ko), idesc_n, 1, leader);        // xs.wb
                     }
                 }
                 tc_commit_lead(empty + st, leader);  // the stage may be refilled once these MMAs have read it
@@ -310,8 +312,14 @@ emission_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * ACC_STRIDE;
 #pragma unroll
-            for (int i = 0; i < NB; ++i) tc_ld16(taddr + 16 * i, v + 16 * i);
-            tc_wait_ld();
+            for (int i = 0; i < NB; ++i) {
+                float lo[16];
+                tc_ld16(taddr + 16 * i, v + 16 * i);
+                tc_ld16(taddr + NPAD + 16 * i, lo);
+                tc_wait_ld();
+#pragma unroll
+                for (int c = 0; c < 16; ++c) v[16 * i + c] += lo[c];
+            }
             tc_fence_before();
             mbar_arrive(tempty + acc);
 

@@ -16,8 +16,8 @@
 // (TileCursor).  One ring stage = one tile:
 //   warp 0      TMA producer: <= 7 boxes of 32 frames x 32 dims of X and one box of 32 frames x 32 weights
 //   warp 1      MMA issuer (one lane): per 8 frames and per half of the feature dims (M = 128) three
-//               tcgen05.mma.kind::tf32 with N = 32 classes; the two accumulators (128 lanes x 32 columns each) stay
-//               in TMEM for the whole kernel
+//               tcgen05.mma.kind::tf32 products in two instructions (xb.[wb|ws] with N = 64, xs.wb with N = 32); the
+//               accumulators (2 feature halves x 128 lanes x 64 columns) stay in TMEM for the whole kernel
 //   warps 2..9  converters: in-place split into big/small, rows behind the end of the video and class columns
 //               >= C forced to zero; at the end warps 2..5 read the accumulators and flush them with atomics.
 // Feature column 255 of every stage holds the constant 1 (chunk slot 7 is never loaded), so that accumulator row
@@ -40,7 +40,7 @@ constexpr int STAGE_BYTES = 2 * XPART + 2 * WPART;  // big + small of X and of t
 constexpr int NSTAGE = 3;
 constexpr int CONV_THREADS = 256;
 constexpr int THREADS = 64 + CONV_THREADS;
-constexpr int TMEM_COLS = 64;
+constexpr int TMEM_COLS = 128;                // 2 feature halves x (NPAD columns x.wb + NPAD columns xb.ws)
 constexpr int NPAD = 32;                     // classes per accumulator (UMMA N)
 constexpr size_t SMEM_BYTES = (size_t)NSTAGE * STAGE_BYTES + 128;
 
@@ -122,13 +122,17 @@ weighted_sums_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
     } else if (warp == 1) {
         // ===================== MMA issuer (whole warp converged, one elected lane issues) =====================
         // D (f32), A = B = tf32, both MN-major, N = 32, M = 128
-        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(NPAD >> 3) << 17) |
-                               ((uint32_t)(128 >> 4) << 24);
+        const uint32_t idesc_n = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(NPAD >> 3) << 17) |
+                                 ((uint32_t)(128 >> 4) << 24);
+        // the big and the small weights lie WPART bytes apart: as one B operand with N = 2 NPAD (LBO = WPART) xb meets
+        // both in a single MMA -- two MMAs per (8 frames, feature half) instead of three
+        const uint32_t idesc_2n = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(2 * NPAD >> 3) << 17) |
+                                  ((uint32_t)(128 >> 4) << 24);
         const uint32_t leader = elect_one();
         const int total_tiles = count_tiles(p.lengths, p.B, TF);
         const int my_tiles = (total_tiles > (int)blockIdx.x) ? (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
         const uint64_t xdesc0 = smem_desc_sw128b32_mn(0, CHUNK_BYTES, 512);   // address field added per MMA
-        const uint64_t wdesc0 = smem_desc_sw128b32_mn(0, 1024, 512);
+        const uint64_t wdesc0 = smem_desc_sw128b32_mn(0, WPART, 512);
         const uint32_t st0 = smem_u32(st_s);
         int st = 0;
         uint32_t ph = 0;
@@ -141,15 +145,13 @@ weighted_sums_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
 #pragma unroll
             for (int ks = 0; ks < TF / 8; ++ks) {
                 const uint64_t wb = desc_at(wdesc0, wb0 + ks * 1024);
-                const uint64_t ws = desc_at(wb, WPART);
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
                     const uint64_t xb = desc_at(xdesc0, xb0 + half * 4 * CHUNK_BYTES + ks * 1024);
                     const uint64_t xs = desc_at(xb, XPART);
-                    const uint32_t d_tmem = tmem_base + half * NPAD;
-                    tc_mma_tf32_lead(d_tmem, xs, wb, idesc, accum, leader);
-                    tc_mma_tf32_lead(d_tmem, xb, ws, idesc, 1, leader);
-                    tc_mma_tf32_lead(d_tmem, xb, wb, idesc, 1, leader);
+                    const uint32_t d_tmem = tmem_base + half * 2 * NPAD;
+                    tc_mma_tf32_lead(d_tmem, xb, wb, idesc_2n, accum, leader);   // xb.[wb | ws]
+                    tc_mma_tf32_lead(d_tmem, xs, wb, idesc_n, 1, leader);        // xs.wb
                 }
                 accum = 1;
             }
@@ -238,11 +240,15 @@ weighted_sums_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
             const int r = q * 32 + lane;
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
-                float v[NPAD];
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + half * NPAD;
+                float v[NPAD], lo[NPAD];
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + half * 2 * NPAD;
                 tc_ld16(taddr, v);
                 tc_ld16(taddr + 16, v + 16);
+                tc_ld16(taddr + NPAD, lo);
+                tc_ld16(taddr + NPAD + 16, lo + 16);
                 tc_wait_ld();
+#pragma unroll
+                for (int c = 0; c < NPAD; ++c) v[c] += lo[c];
                 const int d = half * 128 + r;
 #pragma unroll
                 for (int c = 0; c < NPAD; ++c) {
