@@ -1,8 +1,6 @@
 // Streaming kernels around the DP (sm_100a): emission scoring, class-weighted feature sums,
 // feature moments, one-hot weights, gold-segmentation score.  All are HBM-bound passes over the
 // (B, Tmax, D) feature tensor or the (B, Tmax, C) score tensor.
-#include <cstdlib>
-
 #include "hsmm_common.cuh"
 
 namespace hsmm {
@@ -394,16 +392,9 @@ int launch_weighted_sums_tc(const float* X, const float* wgt, int ldc, const int
 int launch_weighted_sums(const float* X, const float* wgt, int ldc, const int32_t* lengths, int B, int Tmax, int D, int C,
                          float* out_wx, float* out_wsum, int num_sms, cudaStream_t st) {
     {
-        // tensor-core path for the shapes it takes (D <= 224, C <= 32, aligned); 1 = not eligible
-        static int use_tc = -1;
-        if (use_tc < 0) {
-            const char* e = getenv("HSMM_WSUMS_TC");
-            use_tc = e ? atoi(e) : 1;
-        }
-        if (use_tc) {
-            const int rc = launch_weighted_sums_tc(X, wgt, ldc, lengths, B, Tmax, D, C, out_wx, out_wsum, num_sms, st);
-            if (rc != 1) return rc;
-        }
+        // tensor-core path for the shapes it takes (D <= 224, C <= 32, aligned); 1 = not eligible -> SIMT kernels below
+        const int rc = launch_weighted_sums_tc(X, wgt, ldc, lengths, B, Tmax, D, C, out_wx, out_wsum, num_sms, st);
+        if (rc != 1) return rc;
     }
     if (D % 4 != 0 || (reinterpret_cast<uintptr_t>(X) & 15) || ldc % 4 != 0 || (reinterpret_cast<uintptr_t>(wgt) & 15)) {
         const int tpv = (Tmax + 31) / 32;

@@ -23,10 +23,6 @@
 //               TMEM lane mapping of tcgen05.ld (lane quarter = warp % 4).
 // A tile is 128 consecutive frames of ONE video (the last tile of a video runs into the padding / the next video's
 // rows, which are scored and dropped); only live tiles exist and they are dealt round-robin to the CTAs (TileCursor).
-#include <cuda.h>
-
-#include <cstdlib>
-
 #include "hsmm_tc.cuh"
 
 namespace hsmm {
@@ -52,7 +48,6 @@ struct Params {
     float* rowterm;
     double* offset;
     const float* row_const;  // device scalar
-    int exp;                 // HSMM_ETC_EXP timing experiments (results invalid when != 0): 1 no conversion, 2 no MMA, 4 no stores
     int cgroups;             // converter groups in use (1 when shared memory is tight, else CONV_GROUPS)
     int B, Tmax, D, C, ldc;
     int npad;     // classes padded to a multiple of 16 (UMMA N)
@@ -182,7 +177,7 @@ emission_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
                 const int ksteps = (ch == p.nchunk - 1) ? klast : 4;
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) {
-                    if (ks < ksteps && !(p.exp & 2)) {
+                    if (ks < ksteps) {
                         const uint32_t ko = ks * 32;  // 8 tf32 = 32 bytes inside the 128-byte swizzle row
                         tc_mma_tf32_lead(d_tmem, desc_at(xb, ko), desc_at(wb, ko), idesc_2n, accum, leader);   // xb.[wb; ws]
                         accum = 1;
@@ -218,7 +213,7 @@ emission_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
                     mbar_wait(full + st, ph);
                     uint8_t* xb = st_s + (size_t)st * STAGE_BYTES + (size_t)r * 128;
                     uint8_t* xs = xb + CHUNK_BYTES;
-                    if (!(p.exp & 1)) {
+                    {
                     float4 x[8];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
@@ -355,7 +350,7 @@ emission_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
                 }
 #pragma unroll
                 for (int c4 = 0; c4 < NPAD / 4; ++c4)
-                    if (c4 * 4 < p.ldc && !(p.exp & 4))
+                    if (c4 * 4 < p.ldc)
                         *reinterpret_cast<float4*>(em_r + c4 * 4) = make_float4(v[c4 * 4], v[c4 * 4 + 1], v[c4 * 4 + 2], v[c4 * 4 + 3]);
                 p.rowterm[row] = rt;
             }
@@ -399,14 +394,15 @@ static bool plan(int D, int C, Plan* pl) {
     if (C > 64 || D % 4 != 0 || D < 4) return false;
     pl->npad = (C + 15) / 16 * 16;
     pl->nchunk = (D + KC - 1) / KC;
-    const size_t cap = 227 * 1024;
-    size_t fixed = 0;
-    for (pl->cgroups = CONV_GROUPS; pl->cgroups >= 1; --pl->cgroups) {
-        fixed = (size_t)pl->nchunk * 2 * pl->npad * 128 + (size_t)(pl->npad + pl->nchunk * KC) * 4 + (3 * MAX_STAGES + 9) * 8 + 16 +
-                2 * (size_t)pl->cgroups * TILE_M * 4;
-        if (fixed + 2 * (size_t)STAGE_BYTES <= cap) break;
-    }
-    if (pl->cgroups < 1) return false;
+    pl->cgroups = CONV_GROUPS;
+    const size_t fixed = (size_t)pl->nchunk * 2 * pl->npad * 128 + (size_t)(pl->npad + pl->nchunk * KC) * 4 + (3 * MAX_STAGES + 9) * 8 + 16 +
+                         2 * (size_t)pl->cgroups * TILE_M * 4;
+    // 8 KB of the 227 KB stay free when the ring still gets three stages: the DP kernels' CTAs (~1-2 KB each) must fit
+    // beside this one (measured: the ring depth beyond three stages does not matter, the TMA pattern alone reaches
+    // 6 TB/s with three -- tools/tma_stream_bench.cu)
+    size_t cap = 227 * 1024;
+    if (fixed + 3 * (size_t)STAGE_BYTES <= cap - 8 * 1024) cap -= 8 * 1024;
+    if (fixed + 2 * (size_t)STAGE_BYTES > cap) return false;
     int ns = (int)((cap - fixed) / STAGE_BYTES);
     if (ns > MAX_STAGES) ns = MAX_STAGES;
     pl->nstage = ns;
@@ -452,20 +448,6 @@ int launch_emission_tc(const float* X, const float* w, const float* bias, const 
     p.bias = bias; p.inv_var = inv_var; p.penalty = penalty; p.lengths = lengths; p.em = em; p.rowterm = rowterm;
     p.offset = offset; p.row_const = row_const; p.B = B; p.Tmax = Tmax; p.D = D; p.C = C; p.ldc = ldc;
     p.npad = pl.npad; p.nchunk = pl.nchunk; p.nstage = pl.nstage; p.cgroups = pl.cgroups;
-    {
-        static int ex = -1;
-        if (ex < 0) {
-            const char* e = getenv("HSMM_ETC_EXP");
-            ex = e ? atoi(e) : 0;
-        }
-        p.exp = ex;
-        static int nst = -1;
-        if (nst < 0) {
-            const char* e = getenv("HSMM_ETC_NSTAGE");
-            nst = e ? atoi(e) : 0;
-        }
-        if (nst >= 2 && nst < p.nstage) p.nstage = nst;
-    }
     const long long max_tiles = (long long)B * ((Tmax + TILE_M - 1) / TILE_M);
     int grid = num_sms < max_tiles ? num_sms : (int)max_tiles;
     if (grid < 1) grid = 1;

@@ -293,6 +293,38 @@ def test_weighted_feature_sums_vs_numpy(B, Tmax, D, C):
     assert np.abs(wsum.cpu().numpy() - ref_ws).max() < 1e-5 * np.abs(ref_ws).max()
 
 
+@pytest.mark.parametrize("B,Tmax,D,C", [(3, 100, 224, 32), (4, 130, 128, 16), (2, 64, 4, 1), (5, 257, 200, 23), (3, 90, 228, 9),
+                                        (2, 70, 200, 33)])
+def test_weighted_feature_sums_tensor_core_edges(B, Tmax, D, C):
+    """The tcgen05 path of hsmm_weighted_feature_sums at the edges of its eligibility (D <= 224, C <= 32; the last two
+    shapes fall to the SIMT kernel), with a zero-length video, and with NaN in every padding frame of the features AND of
+    the weights: frames t >= length must not reach the sums (the reference only ever sums the first length_b frames,
+    semimarkov_utils.py:74-126)."""
+    import action_segmentation_b200 as pkg
+    rng = np.random.default_rng(7 * B + Tmax + D + C)
+    lengths = rng.integers(1, Tmax + 1, size=B)
+    lengths[0] = Tmax
+    if B > 2:
+        lengths[1] = 0
+    X = rng.normal(size=(B, Tmax, D)).astype(np.float32)
+    ldc = pkg.hsmm.ldc_of(C)
+    wgt = np.zeros((B, Tmax, ldc), dtype=np.float32)
+    wgt[:, :, :C] = rng.dirichlet(np.ones(C), size=(B, Tmax))
+    ref_wx = np.zeros((C, D))
+    ref_ws = np.zeros(C)
+    for b, T in enumerate(lengths):
+        ref_wx += wgt[b, :T, :C].astype(np.float64).T @ X[b, :T].astype(np.float64)
+        ref_ws += wgt[b, :T, :C].astype(np.float64).sum(axis=0)
+        X[b, T:] = np.nan
+        wgt[b, T:] = np.nan
+    li = torch.from_numpy(lengths).to(torch.int32).cuda()
+    wx, wsum = pkg.hsmm.weighted_feature_sums(torch.from_numpy(X).cuda(), torch.from_numpy(wgt).cuda(), C, li)
+    scale = np.sqrt(float(lengths.sum()))
+    assert np.isfinite(wx.cpu().numpy()).all() and np.isfinite(wsum.cpu().numpy()).all()
+    assert np.abs(wx.cpu().numpy() - ref_wx).max() < 2e-5 * scale
+    assert np.abs(wsum.cpu().numpy() - ref_ws).max() < 1e-5 * np.abs(ref_ws).max()
+
+
 def test_supervised_fit_golden(golden):
     """fit_supervised closed form (semimarkov_modules.py:195-256) against the reference's fitted parameters."""
     import action_segmentation_b200 as pkg
