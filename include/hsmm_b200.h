@@ -148,7 +148,11 @@ int hsmm_logz_backward(const float* em, int ldc, const float* init, const float*
  * r^T X of semimarkov_sufficient_stats (semimarkov_utils.py:74-126):
  *   out_wx (C,D)  += sum_{b,t<len_b} weights[b,t,c] * X[b,t,:]
  *   out_wsum (C)  += sum_{b,t<len_b} weights[b,t,c]
- * weights (B,Tmax,ldc).  Both outputs are accumulated into (caller zeroes them).
+ * weights (B,Tmax,ldc).  Both outputs are accumulated into (caller zeroes them).  Frames t >= lengths[b] are never
+ * read into the sums, whatever they hold (NaN included), in X or in weights.
+ * Eligible shapes (D <= 224, D % 4 == 0, C <= 32, ldc % 4 == 0, X and weights 16-byte aligned) run on the tensor cores
+ * (TMA-fed tcgen05.mma over MN-major tf32 operands, 3xTF32 so that the sums are fp32-accurate); the others on a SIMT
+ * fp32 kernel.
  */
 int hsmm_weighted_feature_sums(const float* X, const float* weights, int ldc, const int32_t* lengths,
                                int B, int Tmax, int D, int C, float* out_wx, float* out_wsum, void* stream);
