@@ -530,12 +530,29 @@ def main():
     except Exception:
         pass
     step_bytes = frames * (8 * D + 8 + pen_bytes)
+    # secondary (compute) ceiling of the dominant kernel, SURVEY 8(d): the DP kernels are bound by FP32 issue, not HBM.
+    # Issue-slot utilisation comes from the committed ncu summaries (a profiler number, never a bench value).
+    compute = None
+    try:
+        import csv
+        names = {"logz_backward": "dp_lin_backward", "logz_forward": "dp_lin_forward", "viterbi": "dp_vit2",
+                 "emission": "emission_tc", "weighted_feature_sums": "weighted_sums"}
+        def issue_pct(path):
+            rows = list(csv.reader(open(os.path.join(ROOT, "profiles", path))))
+            col = rows[0].index("smsp__issue_active.avg.pct_of_peak_sustained_active")
+            v = [float(r[col]) for r in rows[2:] if names[dom] in r[0]]
+            return sum(v) / len(v) if v else None
+        compute = {"bound": "fp32_issue", "issue_active_pct_in_step_launch": issue_pct("r01m_ncu_bench_top_summary.csv"),
+                   "issue_active_pct_saturated_launch": issue_pct("r01d_ncu_dp_saturated_summary.csv"),
+                   "source": "profiles/r01m_ncu_bench_top_summary.csv, profiles/r01d_ncu_dp_saturated_summary.csv (ncu)"}
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_frame": bpf,
                 "kernel_ms": {k: round(v, 3) for k, v in kms.items()}, "launches_per_step": klaunch,
                 # whole step against the same peak, per GPU (step_bytes counts this rank's frames)
                 "step_achieved_gbs": step_bytes / (ms_per_step * 1e-3) / 1e9,
-                "step_frac": step_bytes / (ms_per_step * 1e-3) / 1e9 / peak_gbs}
+                "step_frac": step_bytes / (ms_per_step * 1e-3) / 1e9 / peak_gbs, "compute_ceiling": compute}
 
     # ---- end to end through the public API -----------------------------------------------------
     e2e = None
