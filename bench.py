@@ -368,10 +368,13 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------
 # CPU arm: the reference's own algorithm (oracle/reference_port.py) on a bounded sample
 # ---------------------------------------------------------------------------------------------
-def cpu_sample(args):
+def cpu_sample(args, passes=1):
+    """Bounded sample of the workload for the CPU legs: about 6 s per video and pass on 16 cores, so the number of videos
+    shrinks with the number of passes (warm-up + timed steps) to keep the whole run within a few minutes."""
     gen = torch.Generator().manual_seed(args.seed)
     steps = 6
-    C, D, K, B = 2 * steps + 1, args.feature_dim, args.max_span, args.cpu_sample_videos
+    C, D, K = 2 * steps + 1, args.feature_dim, args.max_span
+    B = max(1, min(args.cpu_sample_videos, 25 // max(1, passes)))
     T = args.cpu_sample_frames
     lengths = torch.randint(max(2 * C, T // 2), T + 1, (B,), generator=gen)
     lengths[0] = T
@@ -397,7 +400,7 @@ def cpu_reference_step(s):
 
 def run_cpu_baseline(args, steps, warmup):
     torch.set_num_threads(os.cpu_count() or 1)
-    s = cpu_sample(args)
+    s = cpu_sample(args, steps + warmup)
     for _ in range(warmup):
         cpu_reference_step(s)
     t0 = time.perf_counter()
