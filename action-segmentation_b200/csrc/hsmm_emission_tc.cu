@@ -34,9 +34,9 @@ using namespace tc;
 constexpr int TILE_M = 128;       // frames per tile = UMMA M
 constexpr int KC = 32;            // floats per chunk = one 128-byte swizzle row
 constexpr int CHUNK_BYTES = TILE_M * KC * 4;  // 16 KB
-constexpr int STAGE_BYTES = 2 * CHUNK_BYTES;  // big + small
-constexpr int CONV_GROUPS = 1;   // converter groups (4 warps each) compiled in; Params::cgroups of them take alternate chunks
-constexpr int THREADS = 64 + 128 * CONV_GROUPS + 128;
+constexpr int STAGE_BYTES = CHUNK_BYTES;      // the landed chunk is the big operand; the remainders go to TMEM
+constexpr int XS_BASE = 256;                  // TMEM columns [256, 256 + 32 nstage): remainders xs of the ring stages (A operand)
+constexpr int THREADS = 64 + 128 + 128;        // producer, MMA issuer, 4 converter warps, 4 epilogue warps
 constexpr int MAX_STAGES = 6;
 
 struct Params {
@@ -48,7 +48,6 @@ struct Params {
     float* rowterm;
     double* offset;
     const float* row_const;  // device scalar
-    int cgroups;             // converter groups in use (1 when shared memory is tight, else CONV_GROUPS)
     int B, Tmax, D, C, ldc;
     int npad;     // classes padded to a multiple of 16 (UMMA N)
     int nchunk;   // ceil(D / 32)
@@ -65,7 +64,7 @@ emission_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
     // small class weights sit behind each other in shared memory, so xb meets both in ONE MMA with N = 2 NPAD: two MMAs
     // per k-step instead of three); the epilogue adds the two halves.  Two accumulators (double buffer).
     constexpr int ACC_STRIDE = 2 * NPAD;
-    constexpr int TMEM_COLS = (4 * NPAD <= 64) ? 64 : (4 * NPAD <= 128 ? 128 : 256);
+    constexpr int TMEM_COLS = 512;   // accumulators in [0, 4 NPAD) <= 256, xs slots behind XS_BASE
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // carve: [W: nchunk x (big NPAD x 128 B, small NPAD x 128 B)] [stages] [bias NPAD] [inv_var nchunk*32] [barriers]
     // (offset arithmetic on the __shared__ symbol keeps the address space visible to the compiler: LDS/STS, not generic LD/ST)
@@ -86,7 +85,7 @@ emission_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
     uint64_t* rfull = wbar + 1;                // converters -> epilogue: row terms of a tile   [2]
     uint64_t* rempty = rfull + 2;              // epilogue -> converters                         [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rempty + 2);
-    float* rowsq_s = reinterpret_cast<float*>(tmem_slot + 4);  // [2][CONV_GROUPS][128]
+    float* rowsq_s = reinterpret_cast<float*>(tmem_slot + 4);  // [2][128]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int klast = (p.D - (p.nchunk - 1) * KC + 7) / 8;  // k-steps (of 8) in the last chunk
@@ -100,7 +99,7 @@ emission_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
         for (int a = 0; a < 2; ++a) {
             mbar_init(tfull + a, 1);
             mbar_init(tempty + a, 128);
-            mbar_init(rfull + a, 128 * p.cgroups);
+            mbar_init(rfull + a, 128);
             mbar_init(rempty + a, 128);
         }
         mbar_init(wbar, 1);
@@ -172,7 +171,7 @@ emission_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
                 mbar_wait(conv + st, ph);
                 tc_fence_after();
                 const uint64_t xb = desc_at(desc0, st0 + st * STAGE_BYTES);
-                const uint64_t xs = desc_at(xb, CHUNK_BYTES);
+                const uint32_t xs = tmem_base + XS_BASE + st * KC;   // 128 lanes x 32 columns of remainders
                 const uint64_t wb = desc_at(desc0, w0 + ch * w_chunk_bytes);   // NPAD rows big, then NPAD rows small
                 const int ksteps = (ch == p.nchunk - 1) ? klast : 4;
 #pragma unroll
@@ -181,7 +180,7 @@ emission_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
                         const uint32_t ko = ks * 32;  // 8 tf32 = 32 bytes inside the 128-byte swizzle row
                         tc_mma_tf32_lead(d_tmem, desc_at(xb, ko), desc_at(wb, ko), idesc_2n, accum, leader);   // xb.[wb; ws]
                         accum = 1;
-                        tc_mma_tf32_lead(d_tmem, desc_at(xs, ko), desc_at(wb, ko), idesc_n, 1, leader);        // xs.wb
+                        tc_mma_tf32_ts_lead(d_tmem, xs + ks * 8, desc_at(wb, ko), idesc_n, 1, leader);        // xs.wb
                     }
                 }
                 tc_commit_lead(empty + st, leader);  // the stage may be refilled once these MMAs have read it
@@ -196,69 +195,54 @@ emission_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
                 accph ^= 1;
             }
         }
-    } else if (warp < 2 + 4 * CONV_GROUPS) {
-        // ===================== converters (CONV_GROUPS x 128 threads, thread <-> frame) =====================
-        const int grp = (warp - 2) >> 2;       // this group converts the chunks with (running chunk index % cgroups) == grp
-        if (grp >= p.cgroups) goto done;
-        const int r = ((warp - 2) & 3) * 32 + lane;  // row inside the tile
+    } else if (warp < 6) {
+        // ===================== converters (128 threads, thread <-> frame = TMEM lane) =====================
+        // x = xb + xs with xb = the 19 upper bits of x: the landed chunk ITSELF is the big operand (kind::tf32 reads the
+        // upper 19 bits of a word and ignores the 13 low mantissa bits -- pinned by the parity tests), and the remainder
+        // xs goes straight from registers to tensor memory, the A operand of the second MMA.  The converters write no
+        // shared memory at all: per 16 KB chunk the port carries TMA 16 + this read 16 + operand reads 16 + 12 KB.
+        const int q = warp & 3;               // TMEM lane quarter this warp may access
+        const int r = q * 32 + lane;          // row inside the tile
         int st = 0;
         uint32_t ph = 0;
         int acc = 0;
         uint32_t accph = 0;
-        int turn = 0;                           // running chunk index modulo CONV_GROUPS
         for (int g = blockIdx.x; cur.locate(g, p.lengths, p.B, TILE_M, vb, vj, vlen); g += gridDim.x) {
             float rowsq = 0.0f;
             for (int ch = 0; ch < p.nchunk; ++ch) {
-                if (turn == grp) {
-                    mbar_wait(full + st, ph);
-                    uint8_t* xb = st_s + (size_t)st * STAGE_BYTES + (size_t)r * 128;
-                    uint8_t* xs = xb + CHUNK_BYTES;
-                    {
-                    float4 x[8];
+                mbar_wait(full + st, ph);
+                const uint8_t* xrow = st_s + (size_t)st * STAGE_BYTES + (size_t)r * 128;
+                float4 x[8];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int pj = (i + r) & 7;        // physical 16-byte slot (rotated: conflict-free)
-                        x[i] = *reinterpret_cast<const float4*>(xb + pj * 16);
-                    }
-                    float q0 = 0.0f, q1 = 0.0f;
+                for (int lj = 0; lj < 8; ++lj)   // logical 16-byte unit lj sits in physical slot lj ^ (r & 7): conflict-free
+                    x[lj] = *reinterpret_cast<const float4*>(xrow + ((lj ^ (r & 7)) * 16));
+                float q0 = 0.0f, q1 = 0.0f;
+                float sm[32];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int lj = ((i + r) & 7) ^ (r & 7);  // logical slot under the 128-byte swizzle
-                        const float4 iv = *reinterpret_cast<const float4*>(iv_s + ch * KC + lj * 4);
-                        q0 = fmaf(x[i].x * x[i].x, iv.x, q0);
-                        q1 = fmaf(x[i].y * x[i].y, iv.y, q1);
-                        q0 = fmaf(x[i].z * x[i].z, iv.z, q0);
-                        q1 = fmaf(x[i].w * x[i].w, iv.w, q1);
-                    }
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int pj = (i + r) & 7;
-                        float4 big, sml;
-                        big.x = __uint_as_float(__float_as_uint(x[i].x) & TF32_MASK);
-                        big.y = __uint_as_float(__float_as_uint(x[i].y) & TF32_MASK);
-                        big.z = __uint_as_float(__float_as_uint(x[i].z) & TF32_MASK);
-                        big.w = __uint_as_float(__float_as_uint(x[i].w) & TF32_MASK);
-                        sml.x = x[i].x - big.x;
-                        sml.y = x[i].y - big.y;
-                        sml.z = x[i].z - big.z;
-                        sml.w = x[i].w - big.w;
-                        *reinterpret_cast<float4*>(xb + pj * 16) = big;
-                        *reinterpret_cast<float4*>(xs + pj * 16) = sml;
-                    }
-                    rowsq += q0 + q1;
-                    }
-                    fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
-                    mbar_arrive(conv + st);
+                for (int lj = 0; lj < 8; ++lj) {
+                    const float4 iv = *reinterpret_cast<const float4*>(iv_s + ch * KC + lj * 4);
+                    q0 = fmaf(x[lj].x * x[lj].x, iv.x, q0);
+                    q1 = fmaf(x[lj].y * x[lj].y, iv.y, q1);
+                    q0 = fmaf(x[lj].z * x[lj].z, iv.z, q0);
+                    q1 = fmaf(x[lj].w * x[lj].w, iv.w, q1);
+                    sm[4 * lj + 0] = x[lj].x - __uint_as_float(__float_as_uint(x[lj].x) & TF32_MASK);
+                    sm[4 * lj + 1] = x[lj].y - __uint_as_float(__float_as_uint(x[lj].y) & TF32_MASK);
+                    sm[4 * lj + 2] = x[lj].z - __uint_as_float(__float_as_uint(x[lj].z) & TF32_MASK);
+                    sm[4 * lj + 3] = x[lj].w - __uint_as_float(__float_as_uint(x[lj].w) & TF32_MASK);
                 }
-                if (++turn == p.cgroups) turn = 0;
+                rowsq += q0 + q1;
+                tc_st32(tmem_base + ((uint32_t)(q * 32) << 16) + XS_BASE + st * KC, sm);
+                tc_wait_st();
+                tc_fence_before();
+                mbar_arrive(conv + st);
                 if (++st == p.nstage) {
                     st = 0;
                     ph ^= 1;
                 }
             }
-            // this group's part of the tile's row terms goes to the epilogue warps (slot = accumulator parity)
+            // the tile's row terms go to the epilogue warps (slot = accumulator parity)
             mbar_wait(rempty + acc, accph ^ 1);
-            rowsq_s[(acc * p.cgroups + grp) * TILE_M + r] = rowsq;
+            rowsq_s[acc * TILE_M + r] = rowsq;
             mbar_arrive(rfull + acc);
             if (++acc == 2) {
                 acc = 0;
@@ -294,8 +278,7 @@ emission_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
 
         for (int g = blockIdx.x; cur.locate(g, p.lengths, p.B, TILE_M, vb, vj, vlen); g += gridDim.x) {
             mbar_wait(rfull + acc, accph);
-            float rowsq = 0.0f;
-            for (int gq = 0; gq < p.cgroups; ++gq) rowsq += rowsq_s[(acc * p.cgroups + gq) * TILE_M + r];
+            const float rowsq = rowsq_s[acc * TILE_M + r];
             mbar_arrive(rempty + acc);
 
             const int t = vj * TILE_M + r;
@@ -365,7 +348,6 @@ emission_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
         }
     }
 
-done:
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
@@ -386,7 +368,7 @@ __global__ void emission_split_w_kernel(const float* __restrict__ w, int C, int 
 }
 
 struct Plan {
-    int npad, nchunk, nstage, cgroups;
+    int npad, nchunk, nstage;
     size_t smem;
 };
 
@@ -394,9 +376,8 @@ static bool plan(int D, int C, Plan* pl) {
     if (C > 64 || D % 4 != 0 || D < 4) return false;
     pl->npad = (C + 15) / 16 * 16;
     pl->nchunk = (D + KC - 1) / KC;
-    pl->cgroups = CONV_GROUPS;
     const size_t fixed = (size_t)pl->nchunk * 2 * pl->npad * 128 + (size_t)(pl->npad + pl->nchunk * KC) * 4 + (3 * MAX_STAGES + 9) * 8 + 16 +
-                         2 * (size_t)pl->cgroups * TILE_M * 4;
+                         2 * (size_t)TILE_M * 4;
     // 8 KB of the 227 KB stay free when the ring still gets three stages: the DP kernels' CTAs (~1-2 KB each) must fit
     // beside this one (measured: the ring depth beyond three stages does not matter, the TMA pattern alone reaches
     // 6 TB/s with three -- tools/tma_stream_bench.cu)
@@ -407,6 +388,8 @@ static bool plan(int D, int C, Plan* pl) {
     if (ns > MAX_STAGES) ns = MAX_STAGES;
     pl->nstage = ns;
     pl->smem = fixed + (size_t)ns * STAGE_BYTES;
+    // the kernel allocates all 512 TMEM columns: never two of its CTAs on one SM (the second would sit in tcgen05.alloc)
+    if (pl->smem < 117 * 1024) pl->smem = 117 * 1024;
     return true;
 }
 
@@ -447,7 +430,7 @@ int launch_emission_tc(const float* X, const float* w, const float* bias, const 
     Params p;
     p.bias = bias; p.inv_var = inv_var; p.penalty = penalty; p.lengths = lengths; p.em = em; p.rowterm = rowterm;
     p.offset = offset; p.row_const = row_const; p.B = B; p.Tmax = Tmax; p.D = D; p.C = C; p.ldc = ldc;
-    p.npad = pl.npad; p.nchunk = pl.nchunk; p.nstage = pl.nstage; p.cgroups = pl.cgroups;
+    p.npad = pl.npad; p.nchunk = pl.nchunk; p.nstage = pl.nstage;
     const long long max_tiles = (long long)B * ((Tmax + TILE_M - 1) / TILE_M);
     int grid = num_sms < max_tiles ? num_sms : (int)max_tiles;
     if (grid < 1) grid = 1;

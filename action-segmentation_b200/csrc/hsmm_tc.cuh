@@ -127,6 +127,36 @@ __device__ __forceinline__ void tc_commit_lead(uint64_t* bar, uint32_t leader) {
         "r"(leader)
         : "memory");
 }
+
+// 32 consecutive 32-bit columns of this thread's TMEM lane (warp w owns lanes 32 (w % 4) .. +31)
+__device__ __forceinline__ void tc_st32(uint32_t taddr, const float* v) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+        "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+        "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+        "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])),
+        "r"(__float_as_uint(v[16])), "r"(__float_as_uint(v[17])), "r"(__float_as_uint(v[18])), "r"(__float_as_uint(v[19])),
+        "r"(__float_as_uint(v[20])), "r"(__float_as_uint(v[21])), "r"(__float_as_uint(v[22])), "r"(__float_as_uint(v[23])),
+        "r"(__float_as_uint(v[24])), "r"(__float_as_uint(v[25])), "r"(__float_as_uint(v[26])), "r"(__float_as_uint(v[27])),
+        "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])), "r"(__float_as_uint(v[31]))
+        : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// A operand from tensor memory (128 lanes x 8 tf32 columns at a_tmem), B from shared memory
+__device__ __forceinline__ void tc_mma_tf32_ts_lead(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accum,
+                                                    uint32_t leader) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p, q;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "setp.ne.b32 q, %5, 0;\n"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accum), "r"(leader)
+        : "memory");
+}
 // descriptor with a new start address: only the low 14-bit address field changes
 __device__ __forceinline__ uint64_t desc_at(uint64_t desc0, uint32_t byte_offset) { return desc0 + (uint64_t)(byte_offset >> 4); }
 
