@@ -6,21 +6,21 @@
 // is a (frames x D) . (D x C) contraction with arithmetic intensity C/2 flop/B: HBM-bound, so the job of
 // the kernel is to stream X exactly once at full bandwidth while the tensor pipe does the flops.
 // Plain TF32 (10-bit mantissa) is NOT accurate enough for the 1e-4 tolerance on the marginals at
-// D = 200, so operands are split in registers into a tf32-exact "big" part and a "small" remainder
-// (x = xb + xs, w = wb + ws) and three MMAs accumulate xb.wb + xs.wb + xb.ws in fp32 (3xTF32: the
-// dropped xs.ws term is ~2^-22 relative).
+// D = 200, so operands are split into a tf32-exact "big" part and a "small" remainder (x = xb + xs, w = wb + ws)
+// and the MMAs accumulate xb.wb + xs.wb + xb.ws in fp32 (3xTF32: the dropped xs.ws term is ~2^-22 relative).
 //
-// Persistent CTAs (one per SM), tile = 128 consecutive rows of the flattened (B*Tmax, D) feature matrix:
-//   warp 0      TMA producer: X chunks of 32 floats (one 128-byte swizzle row per frame) into a ring
-//   warp 1      MMA issuer (one lane) + TMEM allocation; 2 accumulators of NPAD columns (double buffer)
-//   warps 2..9  "converters", two groups of four warps that take alternate chunks of the ring: split the landed
-//               chunk into big/small in place (+ this group's part of the row term -0.5 sum x^2/var, handed to
-//               the epilogue warps through shared memory).  Thread <-> frame; all eight 16-byte loads of a row are
-//               issued before the first store (the swizzled slots alias for the compiler, so interleaved
-//               load/store code serialises on the shared-memory latency).
-//   warps 10..13 epilogue (TMEM -> registers: bias, penalty, per-frame shift, row term, f64 per-video offset),
-//               concurrently with the conversion of the following tiles.  Thread <-> frame, which is also the
-//               TMEM lane mapping of tcgen05.ld (lane quarter = warp % 4).
+// Persistent CTAs (one per SM), 320 threads:
+//   warp 0      TMA producer: X chunks of 128 frames x 32 floats (one 128-byte swizzle row per frame) into a ring
+//   warp 1      MMA issuer (whole warp converged, one elected lane issues) + TMEM allocation.  Per k-step of 8 floats:
+//               xb.[wb; ws] with A = the landed chunk in shared memory and N = 2 NPAD, then xs.wb with A = the
+//               remainders in TENSOR MEMORY and N = NPAD.  Two accumulators of 2 NPAD columns (double buffer).
+//   warps 2..5  converters, thread <-> frame <-> TMEM lane: read the landed row once (conflict-free through the
+//               swizzle), accumulate the row term -0.5 sum x^2/var (handed to the epilogue warps through shared
+//               memory) and store the remainders xs = x - (x & 0xffffe000) with tcgen05.st into the stage's 32 TMEM
+//               columns.  They write no shared memory: the chunk itself is the big operand (kind::tf32 ignores the 13
+//               low mantissa bits of a word, which the parity tests pin).
+//   warps 6..9  epilogue (TMEM -> registers: the two accumulator halves added, bias, penalty, per-frame shift, row
+//               term, f64 per-video offset), concurrently with the conversion of the following tiles.
 // A tile is 128 consecutive frames of ONE video (the last tile of a video runs into the padding / the next video's
 // rows, which are scored and dropped); only live tiles exist and they are dealt round-robin to the CTAs (TileCursor).
 #include "hsmm_tc.cuh"
