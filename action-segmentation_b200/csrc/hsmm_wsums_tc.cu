@@ -18,8 +18,9 @@
 //   warp 1      MMA issuer (one lane): per 8 frames and per half of the feature dims (M = 128) three
 //               tcgen05.mma.kind::tf32 products in two instructions (xb.[wb|ws] with N = 64, xs.wb with N = 32); the
 //               accumulators (2 feature halves x 128 lanes x 64 columns) stay in TMEM for the whole kernel
-//   warps 2..9  converters: in-place split into big/small, rows behind the end of the video and class columns
-//               >= C forced to zero; at the end warps 2..5 read the accumulators and flush them with atomics.
+//   warps 2..9  converters: remainders xs = x - (x & 0xffffe000) into the stage's second half (the landed chunk itself is
+//               the big operand), weights split in place, rows behind the end of the video and class columns >= C
+//               forced to zero; at the end warps 2..5 read the accumulators and flush them with atomics.
 // Feature column 255 of every stage holds the constant 1 (chunk slot 7 is never loaded), so that accumulator row
 // 255 is the column sum of the weights (out_wsum).
 #include "hsmm_tc.cuh"
@@ -203,7 +204,9 @@ weighted_sums_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
                     sml.y = v.y - big.y;
                     sml.z = v.z - big.z;
                     sml.w = v.w - big.w;
-                    *reinterpret_cast<float4*>(sb + (size_t)u * 16) = big;
+                    // the landed chunk itself is the big operand (kind::tf32 ignores the 13 low mantissa bits of a word);
+                    // only rows behind the end of the video are overwritten (with zeros: they may hold anything)
+                    if (!xlive) *reinterpret_cast<float4*>(sb + (size_t)u * 16) = big;
                     *reinterpret_cast<float4*>(sb + XPART + (size_t)u * 16) = sml;
                 }
             }
