@@ -2,9 +2,10 @@
 
 Package directory is `action-segmentation_b200/`; import it as `action_segmentation_b200` (the
 repo-root shim of that name loads this directory)."""
-from . import _lib, hsmm, semimarkov_utils  # noqa: F401
+from . import _lib, evaluation, hsmm, semimarkov_utils  # noqa: F401
+from .args import HsmmArgs  # noqa: F401
 from ._lib import HsmmError  # noqa: F401
 from .semimarkov import SemiMarkovModel  # noqa: F401
 from .semimarkov_modules import HsmmScores, SemiMarkovModule  # noqa: F401
 
-__all__ = ["SemiMarkovModule", "SemiMarkovModel", "HsmmScores", "HsmmError", "hsmm", "semimarkov_utils"]
+__all__ = ["SemiMarkovModule", "SemiMarkovModel", "HsmmScores", "HsmmError", "HsmmArgs", "hsmm", "semimarkov_utils", "evaluation"]

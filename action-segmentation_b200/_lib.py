@@ -10,7 +10,7 @@ LIB_PATH = os.path.join(HERE, "libhsmm_b200.so")
 EXPORTS = [
     "hsmm_version", "hsmm_last_error", "hsmm_emission", "hsmm_emission_workspace_bytes", "hsmm_viterbi_workspace_bytes", "hsmm_logz_saved_bytes",
     "hsmm_viterbi", "hsmm_logz_forward", "hsmm_logz_backward", "hsmm_weighted_feature_sums", "hsmm_gold_score",
-    "hsmm_feature_moments", "hsmm_onehot_weights", "hsmm_dp_variant", "hsmm_launch_count", "hsmm_set_linear_window",
+    "hsmm_feature_moments", "hsmm_onehot_weights", "hsmm_dp_variant", "hsmm_launch_count", "hsmm_set_linear_window", "hsmm_set_generic_dp",
 ]
 
 _lib = None
@@ -38,6 +38,8 @@ def load():
     lib.hsmm_dp_variant.argtypes = [i, i, i, i]
     lib.hsmm_set_linear_window.restype = i
     lib.hsmm_set_linear_window.argtypes = [i]
+    lib.hsmm_set_generic_dp.restype = i
+    lib.hsmm_set_generic_dp.argtypes = [i]
     lib.hsmm_viterbi_workspace_bytes.restype = sz
     lib.hsmm_viterbi_workspace_bytes.argtypes = [i, i, i, i]
     lib.hsmm_logz_saved_bytes.restype = sz
@@ -70,6 +72,11 @@ def launch_count():
 
 def dp_variant(C, K, mode, sparse=False, f64_state=False):
     return load().hsmm_dp_variant(int(C), int(K), int(mode), int(bool(sparse)) | (2 if f64_state else 0)).decode()
+
+
+def set_generic_dp(force):
+    """Send every DP call to the general kernels (hsmm_set_generic_dp); returns the previous setting."""
+    return bool(load().hsmm_set_generic_dp(int(bool(force))))
 
 
 def set_linear_window(enabled):

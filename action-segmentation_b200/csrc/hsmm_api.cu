@@ -1,6 +1,7 @@
 // C-ABI of libhsmm_b200.so (see include/hsmm_b200.h).  Argument checking, variant dispatch, error
 // reporting.  No allocation, no synchronisation: every call enqueues kernels on the caller's stream.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/hsmm_b200.h"
@@ -44,6 +45,38 @@ bool dp_lin_used(int C, int L, int mode, bool sparse, bool xp);
 int dp_lin_set_enabled(int on);
 const char* dp_reg_name(int C, int L, int mode, bool sparse, bool xp);
 int dp_reg_launch(DpParams p, int mode, cudaStream_t st);
+size_t dp_gen_scratch_bytes(int C, int L);
+bool dp_gen_shape_ok(int C);
+int dp_gen_launch(DpParams p, int mode, void* scratch, cudaStream_t st);
+
+// HSMM_FORCE_GENERIC=1 / hsmm_set_generic_dp(1): every DP call takes the general kernels (tests, A/B runs)
+static std::atomic<int> g_force_gen{-1};
+static bool force_gen() {
+    int v = g_force_gen.load(std::memory_order_relaxed);
+    if (v < 0) {
+        const char* e = getenv("HSMM_FORCE_GENERIC");
+        v = (e && e[0] == '1') ? 1 : 0;
+        g_force_gen.store(v, std::memory_order_relaxed);
+    }
+    return v == 1;
+}
+// does the call (mode, hint, precision) run on the general kernels?
+static bool use_gen(int C, int L, int mode, bool sparse, bool xp) {
+    return force_gen() || !dp_reg_supported(C, L, mode, sparse, xp);
+}
+// could ANY call on this shape need the general kernels' scratch area?  (the size queries do not know the hints)
+static bool may_use_gen(int C, int L, bool logz, bool xp) {
+    if (force_gen()) return true;
+    for (int sparse = 0; sparse < 2; ++sparse) {
+        if (logz) {
+            if (!dp_reg_supported(C, L, 1, sparse, xp) || !dp_reg_supported(C, L, 2, sparse, xp)) return true;
+        } else if (!dp_reg_supported(C, L, 0, sparse, false)) {
+            return true;
+        }
+    }
+    return false;
+}
+static size_t align256(size_t n) { return (n + 255) / 256 * 256; }
 int launch_emission(const float*, const float*, const float*, const float*, const float*, const float*, const int32_t*, int, int, int,
                     int, int, float*, float*, double*, cudaStream_t);
 size_t emission_tc_workspace_bytes(int D, int C);
@@ -117,28 +150,41 @@ uint64_t hsmm_launch_count(void) { return g_launches.load(); }
 
 const char* hsmm_dp_variant(int C, int K, int mode, int flags) {
     const int L = K - 1;
-    const bool sparse = (flags & 1) != 0, xp = (flags & 2) != 0 && mode != 0;
-    if (dp_reg_supported(C, L, mode, sparse, xp)) {
+    const bool sparse = (flags & HSMM_VARIANT_SPARSE) != 0, xp = (flags & HSMM_VARIANT_F64_STATE) != 0 && mode != 0;
+    if (!use_gen(C, L, mode, sparse, xp)) {
         const char* nm = dp_reg_name(C, L, mode, sparse, xp);
         if (!dp_lin_used(C, L, mode, sparse, xp)) return nm;
         static thread_local char buf[160];
         snprintf(buf, sizeof(buf), "lin+%s", nm);
         return buf;
     }
-    return "unsupported";
+    return dp_gen_shape_ok(C) ? "general (one CTA per video, f64 prefix-sum window in global memory)" : "unsupported";
+}
+
+int hsmm_set_generic_dp(int force) {
+    const int prev = force_gen() ? 1 : 0;
+    g_force_gen.store(force ? 1 : 0, std::memory_order_relaxed);
+    return prev;
 }
 
 int hsmm_set_linear_window(int enabled) { return dp_lin_set_enabled(enabled); }
 
-size_t hsmm_viterbi_workspace_bytes(int B, int Tmax, int C, int K) {
-    (void)K;
+static size_t viterbi_base_bytes(int B, int Tmax, int C) {
     // [beta / back-pointer plane][predecessor plane][normaliser increments (B, Tmax+1)][flags (B)]
     return 2 * plane_elems(B, Tmax, C) * sizeof(uint32_t) + ((size_t)B * (Tmax + 1) + (size_t)B) * sizeof(float);
 }
 
+size_t hsmm_viterbi_workspace_bytes(int B, int Tmax, int C, int K) {
+    size_t n = align256(viterbi_base_bytes(B, Tmax, C));
+    if (K >= 2 && may_use_gen(C, K - 1, false, false)) n += dp_gen_scratch_bytes(C, K - 1);  // general kernels' scratch
+    return n;
+}
+
 size_t hsmm_logz_saved_bytes(int B, int Tmax, int C, int K, int flags) {
-    (void)K;
-    return saved_bytes(B, Tmax, C, (flags & HSMM_FLAG_F64_STATE) != 0);
+    const bool xp = (flags & HSMM_FLAG_F64_STATE) != 0;
+    size_t n = align256(saved_bytes(B, Tmax, C, xp));
+    if (K >= 2 && may_use_gen(C, K - 1, true, xp)) n += dp_gen_scratch_bytes(C, K - 1);
+    return n;
 }
 
 int hsmm_emission(const float* X, const float* w, const float* bias, const float* inv_var, const float* row_const,
@@ -190,9 +236,8 @@ int hsmm_viterbi(const float* em, int ldc, const float* init, const float* trans
     p.vdelta = reinterpret_cast<float*>(p.vpred + plane_elems(B, Tmax, C));
     p.vflag = p.vdelta + (size_t)B * (Tmax + 1);
     p.score = out_score; p.trans_pred = trans_pred;
-    if (dp_reg_supported(C, p.L, 0, trans_pred != nullptr, false)) return dp_reg_launch(p, 0, (cudaStream_t)stream);
-    set_error("hsmm_viterbi: shape C=%d K=%d exceeds on-chip capacity", C, K);
-    return HSMM_ERR_SHAPE;
+    if (!use_gen(C, p.L, 0, trans_pred != nullptr, false)) return dp_reg_launch(p, 0, (cudaStream_t)stream);
+    return dp_gen_launch(p, 0, reinterpret_cast<char*>(workspace) + align256(viterbi_base_bytes(B, Tmax, C)), (cudaStream_t)stream);
 }
 
 int hsmm_logz_forward(const float* em, int ldc, const float* init, const float* trans, const int32_t* trans_pred, const float* lenp,
@@ -217,10 +262,8 @@ int hsmm_logz_forward(const float* em, int ldc, const float* init, const float* 
     p.fbeta = s.fbeta; p.fgamma = s.fgamma; p.fdelta = s.fdelta; p.logz2 = s.logz2; p.fflag = s.fflag; p.bflag = s.bflag;
     p.logz = out_logz;
     p.trans_pred = trans_pred;
-    if (!dp_reg_supported(C, p.L, 1, trans_pred != nullptr, p.xp != 0)) {
-        set_error("hsmm_logz_forward: shape C=%d K=%d not supported (register-resident DP only)", C, K);
-        return HSMM_ERR_SHAPE;
-    }
+    if (use_gen(C, p.L, 1, trans_pred != nullptr, p.xp != 0))
+        return dp_gen_launch(p, 1, reinterpret_cast<char*>(saved) + align256(saved_bytes(B, Tmax, C, p.xp != 0)), (cudaStream_t)stream);
     return dp_reg_launch(p, 1, (cudaStream_t)stream);
 }
 
@@ -233,6 +276,10 @@ int hsmm_logz_backward(const float* em, int ldc, const float* init, const float*
     }
     int rc = check_dims("hsmm_logz_backward", B, Tmax, C, K, ldc);
     if (rc) return rc;
+    if (ldc != (C + 3) / 4 * 4) {  // the saved planes are laid out with this stride
+        set_error("hsmm_logz_backward: ldc must be C rounded up to a multiple of 4 (got %d for C=%d)", ldc, C);
+        return HSMM_ERR_SHAPE;
+    }
     DpParams p;
     memset(&p, 0, sizeof(p));
     p.em = em; p.init = init; p.trans = trans; p.lenp = lenp; p.end = end;
@@ -242,10 +289,9 @@ int hsmm_logz_backward(const float* em, int ldc, const float* init, const float*
     p.fbeta = s.fbeta; p.fgamma = s.fgamma; p.fdelta = s.fdelta; p.logz2 = s.logz2; p.fflag = s.fflag; p.bflag = s.bflag;
     p.trans_succ = trans_succ;
     p.grad = grad_logz; p.d_init = d_init; p.d_trans = d_trans; p.d_len = d_len; p.d_em = d_em;
-    if (!dp_reg_supported(C, p.L, 2, trans_succ != nullptr, p.xp != 0)) {
-        set_error("hsmm_logz_backward: shape C=%d K=%d not supported (register-resident DP only)", C, K);
-        return HSMM_ERR_SHAPE;
-    }
+    if (use_gen(C, p.L, 2, trans_succ != nullptr, p.xp != 0))
+        return dp_gen_launch(p, 2, reinterpret_cast<char*>(const_cast<void*>(saved)) + align256(saved_bytes(B, Tmax, C, p.xp != 0)),
+                             (cudaStream_t)stream);
     return dp_reg_launch(p, 2, (cudaStream_t)stream);
 }
 

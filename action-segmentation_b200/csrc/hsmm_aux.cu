@@ -506,10 +506,15 @@ gold_score_kernel(const float* __restrict__ em, int ldc, const float* __restrict
         for (int i = lane; i < Tmax * ldc; i += 32) dem[i] = 0.0f;
     __syncwarp();
     double acc = 0.0;
+    // A gold segmentation the model cannot score -- a start label outside [0, C) (the wrapper writes -2 for global ids
+    // that are not valid classes of the batch), frame 0 not a segment start, a segment longer than K-1 -- makes the
+    // reference raise inside struct.to_parts / score (semimarkov_modules.py:626-655); here the video's score is NaN.
+    bool bad = false;
     int cur_c = -1, cur_s = 0;  // running segment (class, start), uniform across the warp
     for (int t0 = 0; t0 < T; t0 += 32) {
         const int t = t0 + lane;
         const int s = (t < T) ? sp[t] : -1;
+        bad |= (s < -1) || (s >= C) || (t == 0 && T > 0 && s < 0);
         const unsigned starts = __ballot_sync(FULL, s >= 0);
         // class and start of the segment covering frame t
         const unsigned upto = starts & (0xffffffffu >> (31 - lane));
@@ -539,6 +544,7 @@ gold_score_kernel(const float* __restrict__ em, int ldc, const float* __restrict
                 } else if (pc >= 0 && pc < C) {
                     const int l = t - ps;
                     acc += (double)trans[(size_t)my_c * C + pc];
+                    bad |= (l > L);
                     if (l >= 1 && l <= L) acc += (double)lenp[(size_t)l * C + pc];
                     if (grad) {
                         atomicAdd(d_trans + (size_t)my_c * C + pc, g);
@@ -556,6 +562,7 @@ gold_score_kernel(const float* __restrict__ em, int ldc, const float* __restrict
     }
     if (lane == 0 && cur_c >= 0 && cur_c < C) {
         const int l = T - cur_s;
+        bad |= (l > L);
         if (l >= 1 && l <= L) {
             acc += (double)lenp[(size_t)l * C + cur_c];
             if (grad) atomicAdd(d_len + (size_t)l * C + cur_c, g);
@@ -563,7 +570,8 @@ gold_score_kernel(const float* __restrict__ em, int ldc, const float* __restrict
         if (end) acc += (double)end[(size_t)b * C + cur_c];
     }
     acc = warp_sum(acc);
-    if (lane == 0) out[b] = acc + (offset ? offset[b] : 0.0);
+    bad = __any_sync(FULL, bad);
+    if (lane == 0) out[b] = bad ? __longlong_as_double(0x7ff8000000000000LL) : acc + (offset ? offset[b] : 0.0);
 }
 
 int launch_gold(const float* em, int ldc, const float* init, const float* trans, const float* lenp, const float* end,

@@ -51,6 +51,21 @@ def allreduce_gradients(parameters, loss, group=None):
     return buf[off]
 
 
+def broadcast_parameters(module, group=None, src=0):
+    """Make every replica start from rank `src`'s parameters and buffers (one packed broadcast)."""
+    rank, world = rank_world(group)
+    if world == 1:
+        return
+    tensors = [p.data for p in module.parameters()] + [b.data for b in module.buffers()]
+    flat = torch.cat([t.reshape(-1).to(torch.float32) for t in tensors])
+    dist.broadcast(flat, src=src, group=group)
+    off = 0
+    for t in tensors:
+        n = t.numel()
+        t.copy_(flat[off:off + n].view_as(t).to(t.dtype))
+        off += n
+
+
 def allreduce_stats(buf, group=None):
     """In-place SUM of a packed statistics buffer (EM sufficient statistics, frame counters)."""
     rank, world = rank_world(group)

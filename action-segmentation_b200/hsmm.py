@@ -202,9 +202,12 @@ class HsmmLogZ(torch.autograd.Function):
               trans and the length table (the tiny parameter transforms stay in torch autograd)."""
 
     @staticmethod
-    def forward(ctx, features, means, cov_diag, penalty, init, trans, lenp, end, lengths_i32, order, sparse=None):
+    def forward(ctx, features, means, cov_diag, penalty, init, trans, lenp, end, lengths_i32, order, sparse=None,
+                em_pack=None):
+        """`em_pack` = (em, rowterm, offset) already computed by `emission_scores` for the same inputs (the combined
+        train + decode call scores the emissions once)."""
         C = means.shape[0]
-        em, rowterm, offset = emission_scores(features, means, cov_diag, penalty, lengths_i32)
+        em, rowterm, offset = emission_scores(features, means, cov_diag, penalty, lengths_i32) if em_pack is None else em_pack
         init_f, trans_f, lenp_f, end_f = _f32(init), _f32(trans), _f32(lenp), _f32(end)
         pred, succ = (None, None) if sparse is None else sparse
         # narration constraints put -1e4 offsets into the scores: keep the per-class DP state in double
@@ -230,7 +233,7 @@ class HsmmLogZ(torch.autograd.Function):
             wx, wsum = weighted_feature_sums(features, d_em, C, lengths_i32)
             d_means = (wx - wsum[:, None] * means) / cov_diag[None, :]
         d_pen = d_em[:, :, :C] if ctx.needs_input_grad[3] else None
-        return None, d_means, None, d_pen, d_init, d_trans, d_len, None, None, None, None
+        return None, d_means, None, d_pen, d_init, d_trans, d_len, None, None, None, None, None
 
 
 class HsmmGoldScore(torch.autograd.Function):

@@ -8,10 +8,18 @@ the reference's `Datasplit` API (`corpus.n_classes`, `feature_dim`, `get_allowed
 models/model.py:42-63), so the reference's own data layer plugs in unchanged; `data.py` provides a
 synthetic stand-in with the same surface.
 
-Multi-GPU: pass `dist_group` (or initialise torch.distributed) and every rank processes its shard
-of each mini-batch; the packed gradient buffer is all-reduced once per optimiser step
-(distributed.py).
+What differs from the reference's wrapper, by design:
+  * batches live on the device after their first use (`DeviceBatchCache`): the reference's BatchSampler
+    (data/corpus.py:613-644) always forms the same batches, so from the second epoch -- and in the
+    per-epoch decode of the training split (main.py:207-218) -- nothing is read, padded or copied again;
+  * `predict` enqueues every batch's Viterbi kernels and result copies (pinned memory) and synchronises
+    ONCE per split instead of once per batch; per-frame labels come from the kernel in global ids;
+  * multi-GPU: every rank takes its shard of each mini-batch and the packed gradient buffer is
+    all-reduced once per optimiser step (distributed.py); parameters are broadcast from rank 0.
+The model object pickles (main.py:234, 248-257, 445-469): process groups, loaders and device caches are
+dropped from the pickled state and rebuilt lazily.
 """
+import pickle
 import time
 
 import numpy as np
@@ -32,6 +40,54 @@ def make_optimizer(args, parameters):
     return opt, scheduler
 
 
+def resolve_data_loader():
+    """Inside the reference tree: its own loader (models/model.py:66-77); otherwise the stand-in."""
+    try:
+        from models.model import make_data_loader
+    except ImportError:
+        from .data import make_data_loader
+    return make_data_loader
+
+
+class DeviceBatchCache:
+    """Batches of a split, resident in HBM after their first use.  Key = the sampler's batch (a tuple of
+    (task, video) keys, data/corpus.py:633-636), so a hit skips `Datasplit.__getitem__`, `padding_colate`
+    and the host->device copy altogether.  CrossTask's PCA features are ~4.4 GB; a B200 has 180 GB."""
+
+    MOVE = ('features', 'gt_single', 'constraints')
+
+    def __init__(self, limit_bytes=64 << 30):
+        self.entries, self.bytes, self.limit = {}, 0, limit_bytes
+        self.hits = self.misses = 0
+
+    def get(self, key, build):
+        e = self.entries.get(key)
+        if e is not None:
+            self.hits += 1
+            return e
+        self.misses += 1
+        e = self.to_device(build())
+        size = sum(v.numel() * v.element_size() for v in e.values() if isinstance(v, torch.Tensor) and v.is_cuda)
+        if self.bytes + size <= self.limit:
+            self.entries[key] = e
+            self.bytes += size
+        return e
+
+    @classmethod
+    def to_device(cls, batch):
+        out = dict(batch)
+        for k in cls.MOVE:
+            if k in out and isinstance(out[k], torch.Tensor) and not out[k].is_cuda:
+                src = out[k]
+                if not src.is_pinned():
+                    try:
+                        src = src.pin_memory()
+                    except RuntimeError:
+                        pass
+                out[k] = src.cuda(non_blocking=True)
+        return out
+
+
 class SemiMarkovModel(object):
     @classmethod
     def add_args(cls, parser):
@@ -44,6 +100,9 @@ class SemiMarkovModel(object):
         parser.add_argument('--sm_train_discriminatively', action='store_true')
         parser.add_argument('--sm_hidden_markov', action='store_true')
         parser.add_argument('--sm_predict_single', action='store_true')
+        # extensions: closed-form EM beside the reference's Adam-on-logZ; device cache switch
+        parser.add_argument('--sm_unsupervised_method', choices=['gradient', 'em'], default='gradient')
+        parser.add_argument('--sm_no_device_cache', action='store_true')
 
     @classmethod
     def from_args(cls, args, train_data, make_data_loader=None):
@@ -84,26 +143,54 @@ class SemiMarkovModel(object):
         self.model = model
         self.ordered_indices_by_task = ordered_indices_by_task
         self.dist_group = dist_group
-        if make_data_loader is None:
-            try:  # inside the reference tree: its own loader (models/model.py:66-77)
-                from models.model import make_data_loader
-            except ImportError:
-                from .data import make_data_loader
-        self._make_data_loader = make_data_loader
-        self.model.cuda()
+        self._make_data_loader = make_data_loader  # None: resolved on every use (never pickled)
+        self._cache = None
+        if torch.cuda.is_available():  # without a GPU the first kernel call raises HsmmError (there is no CPU path)
+            self.model.cuda()
 
+    # -- pickling (main.py:234 pickles the model every epoch; :248-257 and :445-469 load it back) -----
     def __getstate__(self):
-        # picklable like the reference's model object (main.py:234): drop the process group / loader fn
         d = dict(self.__dict__)
         d['dist_group'] = None
         d['_make_data_loader'] = None
+        d['_cache'] = None
         return d
 
-    # -- helpers shared by fit / predict --------------------------------------------------------
+    def __setstate__(self, d):
+        self.__dict__.update(d)
+        self.__dict__.setdefault('dist_group', None)
+        self.__dict__.setdefault('_make_data_loader', None)
+        self.__dict__.setdefault('_cache', None)
+        if torch.cuda.is_available():
+            self.model.cuda()
+
+    # -- data plumbing --------------------------------------------------------------------------------
+    def _loader(self, datasplit, **kw):
+        fn = self._make_data_loader or resolve_data_loader()
+        return fn(self.args, datasplit, **kw)
+
+    def _device_batches(self, datasplit, loader):
+        """Iterate `loader`, yielding batch dicts whose tensors are on the device.  With a batch sampler and a
+        map-style dataset (the reference's DataLoader, data.py's stand-in) batches are served from the device
+        cache after their first use."""
+        sampler = getattr(loader, 'batch_sampler', None)
+        dataset = getattr(loader, 'dataset', None)
+        collate = getattr(loader, 'collate_fn', None)
+        if getattr(self.args, 'sm_no_device_cache', False) or sampler is None or dataset is None or collate is None:
+            for batch in loader:
+                yield DeviceBatchCache.to_device(batch)
+            return
+        if self._cache is None:
+            self._cache = DeviceBatchCache()
+        for keys in sampler:
+            keys = list(keys)
+            ck = (id(datasplit), tuple(keys))
+            yield self._cache.get(ck, lambda: collate([dataset[k] for k in keys]))
+
     def fit_supervised(self, train_data):
         # models/semimarkov/semimarkov.py:125-133
         assert not self.args.sm_constrain_transitions
-        loader = self._make_data_loader(self.args, train_data, batch_by_task=False, shuffle=False, batch_size=1)
+        loader = self._loader(train_data, batch_by_task=False, shuffle=False, batch_size=1)
         features, labels = [], []
         for batch in loader:
             features.append(batch['features'].squeeze(0))
@@ -126,18 +213,23 @@ class SemiMarkovModel(object):
         task_indices = [int(x) for x in task_indices.cpu()]
         step_indices = datasplit.get_ordered_indices_no_background()[task]
         assert constraints.size(2) == len(step_indices)
-        expanded = torch.zeros((constraints.size(0), constraints.size(1), len(task_indices)))
-        cols = torch.as_tensor([task_indices.index(label) for label in step_indices], dtype=torch.long)
+        expanded = torch.zeros((constraints.size(0), constraints.size(1), len(task_indices)), device=constraints.device)
+        cols = torch.as_tensor([task_indices.index(label) for label in step_indices], dtype=torch.long,
+                               device=constraints.device)
         expanded[:, :, cols] = constraints
         return expanded
 
     def _narration(self, datasplit, batch, which):
+        """Additive narration penalty (B, T, C) of models/semimarkov/semimarkov.py:227-234, 341-348; built on the device
+        and kept in the (cached) batch dict."""
         if which not in self.args.sm_constrain_with_narration:
             return None
-        tasks = batch['task_name']
-        assert all_equal(tasks)
-        c = self.expand_constraints(datasplit, tasks[0], batch['task_indices'][0], 1 - batch['constraints'])
-        return (c * self.args.sm_constrain_narration_weight).cuda(non_blocking=True)
+        if '_narration_penalty' not in batch:
+            tasks = batch['task_name']
+            assert all_equal(tasks)
+            c = self.expand_constraints(datasplit, tasks[0], batch['task_indices'][0], 1 - batch['constraints'])
+            batch['_narration_penalty'] = (c * self.args.sm_constrain_narration_weight).cuda()
+        return batch['_narration_penalty']
 
     # -- training -------------------------------------------------------------------------------
     def fit(self, train_data, use_labels, callback_fn=None):
@@ -155,20 +247,29 @@ class SemiMarkovModel(object):
                     callback_fn(-1, {})
             else:
                 return
+        if getattr(args, 'sm_init_non_projection_parameters_from', None):
+            initialize = False  # parameters came from the pickled model (SemiMarkovModule.__init__)
+            if callback_fn:
+                callback_fn(-1, {})
         optimizer, scheduler = make_optimizer(args, self.model.parameters())
         if initialize:
-            big = next(iter(self._make_data_loader(args, train_data, batch_by_task=False, shuffle=True, batch_size=100)))
+            big = next(iter(self._loader(train_data, batch_by_task=False, shuffle=True, batch_size=100)))
             self.model.initialize_gaussian(big['features'].cuda(), big['lengths'])
-        loader = self._make_data_loader(args, train_data, batch_by_task=True, shuffle=True, batch_size=args.batch_size)
-        K = args.sm_max_span_length
         rank, world = hdist.rank_world(self.dist_group)
+        # replicas must start identical: init_logits is drawn per process (semimarkov_modules.py:159)
+        hdist.broadcast_parameters(self.model, self.dist_group)
+        if not use_labels and getattr(args, 'sm_unsupervised_method', 'gradient') == 'em':
+            return self._fit_em(train_data, callback_fn)
+        loader = self._loader(train_data, batch_by_task=True, shuffle=True, batch_size=args.batch_size)
+        K = args.sm_max_span_length
+        dev = self.model.gaussian_means.device
         for epoch in range(args.epochs):
             start_time = time.time()
             self.model.train()
             losses, pending = [], []
+            weights = []
             num_frames = num_videos = 0
-            train_nll = 0.0
-            for batch_ix, batch in enumerate(loader):
+            for batch_ix, batch in enumerate(self._device_batches(train_data, loader)):
                 if getattr(args, 'train_limit', None) and batch_ix >= args.train_limit:
                     break
                 tasks, lengths = batch['task_name'], batch['lengths']
@@ -176,39 +277,56 @@ class SemiMarkovModel(object):
                 num_frames += int(lengths.sum())
                 num_videos += len(lengths)
                 addl = self.make_additional_allowed_ends(tasks, lengths)
-                # data-parallel shard of the mini-batch (videos are independent given the parameters)
+                # data-parallel shard of the mini-batch (videos are independent given the parameters); a rank
+                # without videos (batch smaller than the world) contributes zero gradients and still joins the all-reduce
                 sel = hdist.shard_indices(len(lengths), rank, world)
-                features = batch['features'][sel].cuda(non_blocking=True)
-                sub_lengths = lengths[sel]
-                spans = None
-                if use_labels:
-                    spans = semimarkov_utils.labels_to_spans(batch['gt_single'][sel].cuda(), max_k=K)
-                ll, log_det = self.model.log_likelihood(
-                    features, sub_lengths, valid_classes_per_instance=[batch['task_indices'][i] for i in sel],
-                    spans=spans, add_eos=True, use_mean_z=use_labels,
-                    additional_allowed_ends_per_instance=None if addl is None else [addl[i] for i in sel],
-                    constraints=None if constraints is None else constraints[sel])
-                # `ll` is the mean over this rank's shard; weight it so that the all-reduced SUM of
-                # gradients equals the gradient of the mean over the whole mini-batch
-                this_loss = -(ll * (len(sel) / float(len(lengths)))) - log_det
-                pending.append(this_loss)
+                if len(sel) > 0:
+                    whole = len(sel) == len(lengths)
+                    features = batch['features'] if whole else batch['features'][sel]
+                    sub_lengths = lengths if whole else lengths[sel]
+                    spans = None
+                    if use_labels:
+                        gt = batch['gt_single'] if whole else batch['gt_single'][sel]
+                        spans = semimarkov_utils.labels_to_spans(gt, max_k=K)
+                    ll, log_det = self.model.log_likelihood(
+                        features, sub_lengths, valid_classes_per_instance=[batch['task_indices'][i] for i in sel],
+                        spans=spans, add_eos=True, use_mean_z=use_labels,
+                        additional_allowed_ends_per_instance=None if addl is None else [addl[i] for i in sel],
+                        constraints=None if constraints is None else (constraints if whole else constraints[sel]))
+                    # `ll` is the mean over this rank's shard; weight it so that the all-reduced SUM of
+                    # gradients equals the gradient of the mean over the whole mini-batch
+                    frac = len(sel) / float(len(lengths))
+                    pending.append(-(ll * frac) - log_det * frac)
+                else:
+                    pending.append(None)
                 if len(pending) >= args.batch_accumulation:
-                    loss = sum(pending) / len(pending)
-                    loss.backward()
+                    live = [p for p in pending if p is not None]
+                    n_pending = len(pending)
                     pending = []
-                    loss_val = hdist.allreduce_gradients(self.model.parameters(), loss.detach(), self.dist_group)
-                    nll = float(loss_val)
-                    losses.append(nll)
-                    train_nll += nll * len(lengths)
+                    if live:
+                        loss = sum(live) / n_pending
+                        loss.backward()
+                        loss_val = loss.detach()
+                    else:
+                        loss_val = torch.zeros((), device=dev)
+                    loss_val = hdist.allreduce_gradients(self.model.parameters(), loss_val, self.dist_group)
+                    losses.append(loss_val.reshape(()))  # stays on the device: one synchronisation per epoch
+                    weights.append(len(lengths))
                     if args.max_grad_norm is not None:
                         torch.nn.utils.clip_grad_norm_(self.model.parameters(), args.max_grad_norm)
                     optimizer.step()
                     self.model.zero_grad()
                     if getattr(args, 'print_every', 0) and batch_ix % args.print_every == 0 and rank == 0:
+                        nll_so_far = float((torch.stack(losses) * torch.tensor(weights, device=dev)).sum())
                         print('Epoch: %02d, Batch: %03d, loss: %.4f, recon: %.4f, Throughput: %.2f vid / sec' % (
-                            epoch, batch_ix, train_nll / max(num_videos, 1), train_nll / max(num_frames, 1),
+                            epoch, batch_ix, nll_so_far / max(num_videos, 1), nll_so_far / max(num_frames, 1),
                             num_videos / (time.time() - start_time)))
-            train_loss = float(np.mean(losses)) if losses else float('nan')
+            if losses:
+                lv = torch.stack(losses).double()
+                train_loss = float(lv.mean())
+                train_nll = float((lv * torch.tensor(weights, device=dev, dtype=torch.float64)).sum())
+            else:
+                train_loss, train_nll = float('nan'), 0.0
             if scheduler is not None:
                 scheduler.step(train_loss)
             if callback_fn:
@@ -217,23 +335,67 @@ class SemiMarkovModel(object):
                                     'train_kl_vid_avg': 0.0,
                                     'train_recon_bound': train_nll / max(num_frames, 1)})
 
+    def _fit_em(self, train_data, callback_fn=None):
+        """Closed-form EM (--sm_unsupervised_method em): one E-step over the split with
+        the same forward/backward kernels, ONE all-reduce of the packed expected counts, closed-form M-step."""
+        args = self.args
+        loader = self._loader(train_data, batch_by_task=True, shuffle=False, batch_size=args.batch_size)
+        rank, world = hdist.rank_world(self.dist_group)
+        for epoch in range(args.epochs):
+            self.model.train()
+            total = None
+            num_frames = 0
+            for batch_ix, batch in enumerate(self._device_batches(train_data, loader)):
+                if getattr(args, 'train_limit', None) and batch_ix >= args.train_limit:
+                    break
+                num_frames += int(batch['lengths'].sum())
+                if batch_ix % world != rank:  # whole batches per rank: the statistics simply add up
+                    continue
+                constraints = self._narration(train_data, batch, 'train')
+                addl = self.make_additional_allowed_ends(batch['task_name'], batch['lengths'])
+                st = self.model.expected_statistics(batch['features'], batch['lengths'], batch['task_indices'],
+                                                    additional_allowed_ends_per_instance=addl, constraints=constraints)
+                total = self.model.add_statistics(total, st)
+            buf = self.model.pack_statistics(total) if total is not None else \
+                torch.zeros(self.model.statistics_size(), device=self.model.gaussian_means.device)
+            buf = hdist.allreduce_stats(buf, self.dist_group)
+            stats = self.model.unpack_statistics(buf)
+            ll = self.model.em_update(stats)
+            if callback_fn:
+                nll = -float(stats['logz'])
+                callback_fn(epoch, {'train_loss': -ll, 'train_nll_frame_avg': nll / max(num_frames, 1),
+                                    'train_kl_vid_avg': 0.0, 'train_recon_bound': nll / max(num_frames, 1)})
+
     # -- decoding -------------------------------------------------------------------------------
     def predict(self, test_data):
-        # models/semimarkov/semimarkov.py:318-410; per-frame labels come straight from the kernel
+        """models/semimarkov/semimarkov.py:318-410.  Per-frame labels (global class ids) come straight from the
+        Viterbi kernel; every batch's kernels and result copies are enqueued back to back and the host
+        synchronises once for the whole split."""
         self.model.eval()
         predictions = {}
-        loader = self._make_data_loader(self.args, test_data, shuffle=False, batch_by_task=True,
-                                        batch_size=self.args.batch_size)
-        for batch in loader:
+        loader = self._loader(test_data, shuffle=False, batch_by_task=True, batch_size=self.args.batch_size)
+        queued = []
+        for batch in self._device_batches(test_data, loader):
             tasks, lengths = batch['task_name'], batch['lengths']
             assert len(set(tasks)) == 1
             constraints = self._narration(test_data, batch, 'test')
             addl = self.make_additional_allowed_ends(tasks, lengths)
-            _, labels = self.model.viterbi(batch['features'].cuda(non_blocking=True), lengths, batch['task_indices'],
+            _, labels = self.model.viterbi(batch['features'], lengths, batch['task_indices'],
                                            add_eos=True, use_mean_z=True, additional_allowed_ends_per_instance=addl,
-                                           constraints=constraints, return_labels=True)
-            for video, lab, n in zip(batch['video_name'], labels, lengths):
-                preds = lab[:int(n)].numpy()
+                                           constraints=constraints, return_labels=True, non_blocking=True,
+                                           return_spans=False)
+            queued.append((batch['video_name'], labels, lengths))
+        torch.cuda.current_stream().synchronize()  # all label copies have landed in pinned memory
+        for videos, labels, lengths in queued:
+            labels = labels.numpy()
+            for video, lab, n in zip(videos, labels, lengths):
+                preds = lab[:int(n)].copy()
                 assert self.model.n_classes not in preds, "predictions should not contain EOS: {}".format(preds)
                 predictions[video] = preds
         return predictions
+
+
+def load_pickled_model(path):
+    """utils/utils.py:load_pickle for a pickled SemiMarkovModel (main.py:445-469)."""
+    with open(path, 'rb') as f:
+        return pickle.load(f)

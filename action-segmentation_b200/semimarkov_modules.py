@@ -11,6 +11,7 @@ differentiated by autograd; the DP gradients come from the library's backward ke
 Not supported (out of scope): the NICE feature projector
 (`--sm_feature_projection`) and the component model.
 """
+import pickle
 from typing import Dict, Set
 
 import numpy as np
@@ -78,6 +79,13 @@ class SemiMarkovModule(nn.Module):
         if getattr(args, 'sm_feature_projection', False):
             raise NotImplementedError("--sm_feature_projection (NICE flow) is outside the B200 hot path")
         self.feature_projector = None
+        init_from = getattr(args, 'sm_init_non_projection_parameters_from', None)
+        if init_from is not None:
+            # semimarkov_modules.py:90-94: start from the parameters of a pickled SemiMarkovModel
+            print("loading all non-flow parameters from {}".format(init_from))
+            with open(init_from, 'rb') as f:
+                sm = pickle.load(f)
+            self.init_nonproject_parameters(sm.model)
         self.max_k = args.sm_max_span_length
         self._merge_classes = merge_classes
         self.kl = None
@@ -86,6 +94,13 @@ class SemiMarkovModule(nn.Module):
     @property
     def merge_classes(self):
         return getattr(self, '_merge_classes', None)
+
+    def init_nonproject_parameters(self, model):
+        # semimarkov_modules.py:125-129 (there is no feature projector here, so nothing may be missing)
+        assert isinstance(model, SemiMarkovModule)
+        incompatible = self.load_state_dict(model.state_dict(), strict=False)
+        assert not incompatible.unexpected_keys, incompatible.unexpected_keys
+        assert not incompatible.missing_keys, incompatible.missing_keys
 
     def init_params(self):
         # semimarkov_modules.py:142-159
@@ -380,7 +395,7 @@ class SemiMarkovModule(nn.Module):
         # gold spans arrive in global class ids; map to positions in valid_classes
         dev = features.device
         spans = spans.to(dev)
-        lut = torch.full((self.n_classes + 1,), -1, dtype=torch.long, device=dev)
+        lut = torch.full((self.n_classes + 1,), -2, dtype=torch.long, device=dev)  # -2: not a valid class -> NaN score
         vc = torch.arange(self.n_classes, device=dev) if s['valid_classes'] is None else s['valid_classes']
         lut[vc] = torch.arange(len(vc), device=dev)
         local = torch.where(spans >= 0, lut[spans.clamp(min=0)], torch.full_like(spans, -1)).to(torch.int32).contiguous()
@@ -438,6 +453,10 @@ class SemiMarkovModule(nn.Module):
     def pack_statistics(cls, stats):
         return torch.cat([stats[k].reshape(-1) for k in cls.STAT_KEYS])
 
+    def statistics_size(self):
+        n, D = self.n_classes, self.feature_dim
+        return n * D + n + n + n * n + n + n + 2
+
     def unpack_statistics(self, buf):
         n, D = self.n_classes, self.feature_dim
         shapes = dict(wx=(n, D), wsum=(n,), init=(n,), trans=(n, n), len_num=(n,), len_den=(n,), logz=(1,), n=(1,))
@@ -482,14 +501,25 @@ class SemiMarkovModule(nn.Module):
                 self.init_logits.data = torch.where(ini > 0, (ini / tot).clamp(min=1e-30).log(), torch.full_like(ini, -30.0))
         return float(stats['logz']) / max(1.0, float(stats['n']))
 
+    @staticmethod
+    def _to_host(t, non_blocking):
+        if t is None:
+            return None
+        if not non_blocking:
+            return t.cpu()
+        h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        h.copy_(t, non_blocking=True)
+        return h
+
     def viterbi(self, features, lengths, valid_classes_per_instance, add_eos=True, use_mean_z=False,
                 additional_allowed_ends_per_instance=None, constraints=None, predict_single=False, return_elp=False,
-                return_labels=False, non_blocking=False):
+                return_labels=False, non_blocking=False, return_spans=True):
         """semimarkov_modules.py:660-696: span-encoded predictions (b x T+1, CPU int64, global class
         ids, EOS = n_classes at position lengths[b]).  `return_labels=True` additionally returns the
         per-frame labels the kernel emits (replacing semimarkov_utils.spans_to_labels).
         `non_blocking=True` copies the results into pinned host memory asynchronously on the current
-        stream: the caller synchronises the stream (or device) before reading them."""
+        stream: the caller synchronises the stream (or device) before reading them.
+        `return_spans=False` skips the device->host copy of the span encoding (first result is None)."""
         assert add_eos, "only add_eos=True is implemented"
         valid_classes, C = self._valid_classes(valid_classes_per_instance)
         with torch.no_grad():
@@ -500,16 +530,29 @@ class SemiMarkovModule(nn.Module):
                                                    scores.offset, scores.lengths_i32, scores.order, scores.decode_ids,
                                                    want_labels=return_labels, want_score=False,
                                                    trans_pred=None if scores.sparse is None else scores.sparse[0])
-        def to_host(t):
-            if not non_blocking:
-                return t.cpu()
-            h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
-            h.copy_(t, non_blocking=True)
-            return h
-
-        out = [to_host(spans)]
+        out = [self._to_host(spans, non_blocking) if return_spans else None]
         if return_elp:
             out.append(scores.elp)
         if return_labels:
-            out.append(to_host(labels))
+            out.append(self._to_host(labels, non_blocking))
         return out[0] if len(out) == 1 else tuple(out)
+
+    def log_likelihood_and_viterbi(self, features, lengths, valid_classes_per_instance, add_eos=True,
+                                   additional_allowed_ends_per_instance=None, constraints=None, non_blocking=False):
+        """`log_likelihood(spans=None)` and `viterbi(return_labels=True)` of the same batch with ONE emission pass
+        (the unsupervised trainer's step followed by the decode of the same videos, main.py:207-218).
+        Returns (ll_mean, log_det_mean, spans, labels); ll_mean carries the same autograd graph as log_likelihood's."""
+        assert add_eos, "only add_eos=True is implemented"
+        valid_classes, C = self._valid_classes(valid_classes_per_instance)
+        self.set_z(features, lengths, use_mean=False)
+        s = self._scores(features, lengths, valid_classes, additional_allowed_ends_per_instance)
+        with torch.no_grad():
+            em_pack = hsmm.emission_scores(features, s['means'], s['cov_diag'], constraints, s['lengths_i32'])
+        logz, _, _ = hsmm.HsmmLogZ.apply(features, s['means'], s['cov_diag'], constraints, s['init'], s['trans'], s['lenp'],
+                                         s['end'], s['lengths_i32'], s['order'], s['sparse'], em_pack)
+        with torch.no_grad():
+            spans, labels, _ = hsmm.viterbi_decode(em_pack[0], C, s['init'], s['trans'], s['lenp'], s['end'], em_pack[2],
+                                                   s['lengths_i32'], s['order'], s['decode_ids'], want_labels=True,
+                                                   want_score=False, trans_pred=None if s['sparse'] is None else s['sparse'][0])
+        log_det = torch.zeros(features.size(0), device=features.device, requires_grad=False)
+        return logz.mean(), log_det.mean(), self._to_host(spans, non_blocking), self._to_host(labels, non_blocking)

@@ -269,7 +269,7 @@ def e2e_step(models, tasks, host, streams):
 
 def build_models(tasks, args):
     import action_segmentation_b200 as pkg
-    from tests.golden.ref_import import RefArgs
+    from action_segmentation_b200.args import HsmmArgs as RefArgs
     models = []
     for tk in tasks:
         C = tk.C

@@ -163,6 +163,8 @@ int hsmm_weighted_feature_sums(const float* X, const float* weights, int ldc, co
  * spans (B,Tmax) int32 in LOCAL class ids, -1 = continuation (semimarkov_utils.labels_to_spans).
  * out_score (B) double (+ offset).  With grad_score != NULL it also accumulates the (one-hot) counts
  * d_init/d_trans/d_len and writes d_em exactly like hsmm_logz_backward.
+ * A segmentation the model cannot score -- a start label < -1 or >= C, frame 0 not a segment start, a segment longer
+ * than K-1 -- gives out_score[b] = NaN (the reference raises inside struct.to_parts / score for those).
  */
 int hsmm_gold_score(const float* em, int ldc, const float* init, const float* trans, const float* lenp,
                     const float* end, const double* offset, const int32_t* lengths, const int32_t* spans,
@@ -183,10 +185,20 @@ int hsmm_onehot_weights(const int32_t* labels, const int32_t* lengths, int B, in
                         float* weights, void* stream);
 
 /* Introspection used by tests/bench: name of the DP kernel variant picked for a shape
- * ("reg<KR,S>/treg", "reg<KR,S>/tsmem", "ring") and how many kernels the library has launched. */
+ * ("reg<KR,S>/...", "lin+reg<...>", "general ...") and how many kernels the library has launched. */
+#define HSMM_VARIANT_SPARSE 1    /* sparse transition lists given */
+#define HSMM_VARIANT_F64_STATE 2 /* HSMM_FLAG_F64_STATE set on the DP call (NOT the same bit as HSMM_FLAG_F64_STATE) */
 const char* hsmm_dp_variant(int C, int K, int mode /*0 viterbi, 1 forward, 2 backward*/,
-                            int flags /* bit 0: sparse transition lists, bit 1: f64 state */);
+                            int flags /* HSMM_VARIANT_* */);
 uint64_t hsmm_launch_count(void);
+
+/* Shapes beyond the register-resident kernels' envelope (hsmm_dp_variant names the kernel family of a shape) run on
+ * general kernels -- one CTA per video, the span window in prefix-sum form in double precision, any K and up to 1024
+ * classes -- so no shape the reference accepts is rejected; C > 1024 returns HSMM_ERR_SHAPE.  The workspace size
+ * queries above already include their scratch area.  hsmm_set_generic_dp(1) (environment: HSMM_FORCE_GENERIC=1,
+ * read before the first call) sends EVERY DP call to the general kernels (tests, A/B runs); set it before
+ * querying workspace sizes.  Returns the previous setting. */
+int hsmm_set_generic_dp(int force);
 
 /* hsmm_logz_forward / hsmm_logz_backward run a linear-window (block floating point) kernel on the shapes that
  * fit one warp per video and recompute the videos it cannot certify with the log-domain kernel; results do not

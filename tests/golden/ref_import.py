@@ -1,23 +1,34 @@
-"""Import the UNMODIFIED reference HSMM modules from /root/reference (this container only).
+"""Import the UNMODIFIED reference modules: from /root/reference (this container) or from the git-ignored
+copy oracle/_ref/src that oracle/make_ref.py makes and gpurun ships to the GPU box.
 
 The reference needs two third-party packages that are not installable here:
   * torch_struct  -> oracle/torch_struct_shim.py (restated algorithm, see its header)
-  * editdistance  -> a tiny pure-Python Levenshtein (only imported, never on the HSMM path)
-Nothing in the -m gpu tests, smoke() or bench.py may call this: /root/reference does not exist
-on the GPU box.  It is used by make_golden.py and by CPU tests that skip when the tree is absent.
+  * editdistance  -> a tiny pure-Python Levenshtein
+and `ReduceLROnPlateau(verbose=...)` (models/model.py:30-36) no longer exists in torch 2.11: the keyword is dropped
+by a wrapper installed on torch.optim.lr_scheduler for the duration of the import context.
+Test / baseline infrastructure only: the product package never imports this.
 """
 import importlib
 import os
 import sys
 import types
 
-REF_ROOT = "/root/reference"
-REF_SRC = os.path.join(REF_ROOT, "src")
 REPO = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+CANDIDATES = ["/root/reference/src", os.path.join(REPO, "oracle", "_ref", "src")]
+
+
+def ref_src():
+    for c in CANDIDATES:
+        if os.path.isdir(os.path.join(c, "models", "semimarkov")):
+            return c
+    return None
+
+
+REF_SRC = ref_src()
 
 
 def reference_available():
-    return os.path.isdir(os.path.join(REF_SRC, "models", "semimarkov"))
+    return ref_src() is not None
 
 
 def _levenshtein(a, b):
@@ -30,10 +41,7 @@ def _levenshtein(a, b):
     return prev[-1]
 
 
-def load_reference():
-    """Returns (semimarkov_modules, semimarkov_utils) of the reference, imported as-is."""
-    if not reference_available():
-        raise RuntimeError("reference tree not present at %s" % REF_ROOT)
+def install_shims():
     if REPO not in sys.path:
         sys.path.insert(0, REPO)
     shim = importlib.import_module("oracle.torch_struct_shim")
@@ -42,23 +50,41 @@ def load_reference():
         ed = types.ModuleType("editdistance")
         ed.eval = _levenshtein
         sys.modules["editdistance"] = ed
-    if REF_SRC not in sys.path:
-        sys.path.insert(0, REF_SRC)
+    import torch
+    sched = torch.optim.lr_scheduler
+    if not getattr(sched.ReduceLROnPlateau, "_hsmm_compat", False):
+        base = sched.ReduceLROnPlateau
+
+        class ReduceLROnPlateau(base):  # accepts and ignores the removed `verbose` keyword
+            _hsmm_compat = True
+
+            def __init__(self, *a, verbose=None, **kw):
+                super().__init__(*a, **kw)
+
+        sched.ReduceLROnPlateau = ReduceLROnPlateau
+    src = ref_src()
+    if src is None:
+        raise RuntimeError("reference sources not found (looked in %s); run `python oracle/make_ref.py` where "
+                           "/root/reference exists" % ", ".join(CANDIDATES))
+    if src not in sys.path:
+        sys.path.insert(0, src)
+    return src
+
+
+def load_reference():
+    """Returns (semimarkov_modules, semimarkov_utils) of the reference, imported as-is."""
+    install_shims()
     mods = importlib.import_module("models.semimarkov.semimarkov_modules")
     utils = importlib.import_module("models.semimarkov.semimarkov_utils")
     return mods, utils
 
 
-class RefArgs:
-    """Minimal argparse namespace the reference module reads (semimarkov_modules.py:54-65,
-    semimarkov.py:16-31)."""
+def load_reference_module(name):
+    """Any other module of the reference's src/ tree, e.g. 'models.semimarkov.semimarkov', 'evaluation.accuracy', 'main'."""
+    install_shims()
+    return importlib.import_module(name)
 
-    def __init__(self, **kw):
-        self.sm_max_span_length = 20
-        self.sm_supervised_state_smoothing = 1e-2
-        self.sm_supervised_length_smoothing = 1e-1
-        self.sm_supervised_method = "closed-form"
-        self.sm_feature_projection = False
-        self.sm_init_non_projection_parameters_from = None
-        self.sm_train_discriminatively = False
-        self.__dict__.update(kw)
+
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+from action_segmentation_b200.args import HsmmArgs as RefArgs  # noqa: E402,F401  (kept under its old name for make_golden.py)

@@ -10,7 +10,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 from oracle import hsmm_oracle as O  # noqa: E402
-from tests.golden.ref_import import RefArgs  # noqa: E402
+from action_segmentation_b200.args import HsmmArgs as RefArgs  # noqa: E402
 
 
 def module_from_golden(g, device="cuda", **argkw):

@@ -1,0 +1,195 @@
+"""GPU parity of (1) the general DP kernels (hsmm_dp_gen.cu: any K, up to 1024 classes -- what runs beyond the
+register-resident envelope) and (2) every kernel family at BASELINE.json's full sizes, against the fp64 oracle."""
+import numpy as np
+import pytest
+import torch
+
+import action_segmentation_b200 as pkg
+from oracle import hsmm_oracle as O
+from tests.helpers import check_viterbi_against_oracle, random_problem, rel_err, sparse_lists, to_dev
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture
+def generic_dp():
+    prev = pkg._lib.set_generic_dp(True)
+    yield
+    pkg._lib.set_generic_dp(prev)
+
+
+def _f32(x):
+    return None if x is None else x.astype(np.float32).astype(np.float64)
+
+
+def run_logz_and_counts(prob, sp=(None, None), f64_state=False, seed=0, fwd_generic=None, bwd_generic=None):
+    d = to_dev(prob)
+    B, _, C = prob["em"].shape
+    if fwd_generic is not None:
+        pkg._lib.set_generic_dp(fwd_generic)
+    logz, saved = pkg.hsmm.logz_forward(d["em"], C, d["init"], d["trans"], d["lenp"], d["end"], None, d["lengths_i32"],
+                                        d["order"], trans_pred=sp[0], f64_state=f64_state)
+    w = np.random.default_rng(seed).uniform(0.5, 1.5, size=B)
+    g = torch.from_numpy(w).float().cuda()
+    if bwd_generic is not None:
+        pkg._lib.set_generic_dp(bwd_generic)
+    d_init, d_trans, d_len, d_em = pkg.hsmm.logz_backward(d["em"], C, d["init"], d["trans"], d["lenp"], d["end"],
+                                                         d["lengths_i32"], d["order"], g, saved, trans_succ=sp[1],
+                                                         f64_state=f64_state)
+    return logz.cpu().numpy(), dict(E_init=d_init, E_trans=d_trans, E_len=d_len, E_em=d_em[:, :, :C]), w
+
+
+def check_against_oracle(prob, logz, counts, w, tol_logz=1e-5, tol=1e-4):
+    ref_logz, acc = O.batch_logz_and_counts(_f32(prob["em"]), prob["lengths"], _f32(prob["init"]), _f32(prob["trans"]),
+                                            _f32(prob["lenp"]), prob["end"], w)
+    assert np.allclose(logz, ref_logz, rtol=tol_logz, atol=1e-4), np.abs(logz - ref_logz).max()
+    for k, v in counts.items():
+        e = rel_err(v.cpu().numpy(), acc[k])
+        assert e < tol, (k, e)
+
+
+GEN_SHAPES = [
+    # (B, Tmax, C, K, chain, ends)
+    (7, 60, 23, 20, True, True),
+    (5, 90, 9, 20, True, True),
+    (4, 150, 11, 100, False, False),
+    (3, 120, 64, 50, False, False),
+    (3, 40, 1, 5, False, False),
+    (4, 12, 4, 40, False, False),    # K clamped to the padded length
+    (2, 70, 40, 7, False, True),     # more classes than span lengths
+]
+
+
+@pytest.mark.parametrize("f64_state", [False, True], ids=["f32planes", "f64planes"])
+@pytest.mark.parametrize("shape", GEN_SHAPES, ids=lambda s: "B%d_T%d_C%d_K%d" % s[:4])
+def test_general_kernels_vs_oracle(generic_dp, shape, f64_state):
+    B, Tmax, C, K, chain, ends = shape
+    assert "general" in pkg._lib.dp_variant(C, K, 2)
+    rng = np.random.default_rng(300 + C * 7 + K)
+    prob = random_problem(rng, B, Tmax, C, K, Tmin=1, chain=chain, ends=ends, narration=chain and f64_state)
+    prob["lenp"] = O.clamp_len_table(prob["lenp"], Tmax)
+    logz, counts, w = run_logz_and_counts(prob, f64_state=f64_state)
+    check_against_oracle(prob, logz, counts, w)
+    d = to_dev(prob)
+    spans, labels, score = pkg.hsmm.viterbi_decode(d["em"], C, d["init"], d["trans"], d["lenp"], d["end"], None,
+                                                   d["lengths_i32"], d["order"])
+    n_exact = check_viterbi_against_oracle(prob, spans.cpu().numpy(), score.cpu().numpy())
+    assert n_exact >= B - 1
+    lab = pkg.semimarkov_utils.spans_to_labels(spans.cpu())
+    for b, T in enumerate(prob["lengths"]):
+        assert (labels[b, :T].cpu() == lab[b, :T]).all() and (labels[b, T:].cpu() == C).all()
+
+
+@pytest.mark.parametrize("fwd_generic,bwd_generic", [(True, False), (False, True)], ids=["gen_fwd+reg_bwd", "reg_fwd+gen_bwd"])
+@pytest.mark.parametrize("f64_state", [False, True], ids=["f32planes", "f64planes"])
+def test_general_and_register_kernels_share_the_saved_format(fwd_generic, bwd_generic, f64_state):
+    """Forward by one kernel family, backward by the other (the saved planes are relative to the same running
+    normaliser): e.g. C = 133 / K = 200, whose forward pass fits the register kernels and whose backward pass does not."""
+    prev = pkg._lib.set_generic_dp(False)
+    try:
+        rng = np.random.default_rng(11)
+        for (B, Tmax, C, K, chain) in [(6, 80, 23, 20, True), (4, 130, 11, 60, False)]:
+            prob = random_problem(rng, B, Tmax, C, K, Tmin=5, chain=chain, ends=chain)
+            prob["lenp"] = O.clamp_len_table(prob["lenp"], Tmax)
+            sp = sparse_lists(prob) if chain else (None, None)
+            logz, counts, w = run_logz_and_counts(prob, sp=sp, f64_state=f64_state, fwd_generic=fwd_generic, bwd_generic=bwd_generic)
+            check_against_oracle(prob, logz, counts, w)
+    finally:
+        pkg._lib.set_generic_dp(prev)
+
+
+@pytest.mark.parametrize("B,Tmax,C,K", [(2, 560, 48, 500), (2, 240, 133, 100), (2, 320, 133, 200), (3, 120, 284, 20),
+                                        (2, 150, 170, 100)])
+def test_backward_beyond_the_register_envelope_vs_oracle(B, Tmax, C, K):
+    """Shapes round 1 rejected (`hsmm_logz_backward` "unsupported"): Breakfast with a large max span (configs[3]),
+    the decode-sweep shapes with gradients (configs[4]) and valid_classes=None over CrossTask's 284 classes."""
+    assert "general" in pkg._lib.dp_variant(C, K, 2)
+    rng = np.random.default_rng(C + K)
+    prob = random_problem(rng, B, Tmax, C, K, Tmin=Tmax // 2, chain=False, ends=False, scale=2.0)
+    prob["lenp"] = O.clamp_len_table(prob["lenp"], Tmax)
+    logz, counts, w = run_logz_and_counts(prob)
+    check_against_oracle(prob, logz, counts, w)
+    d = to_dev(prob)
+    spans, _, score = pkg.hsmm.viterbi_decode(d["em"], C, d["init"], d["trans"], d["lenp"], d["end"], None,
+                                              d["lengths_i32"], d["order"])
+    assert check_viterbi_against_oracle(prob, spans.cpu().numpy(), score.cpu().numpy()) >= B - 1
+
+
+def test_module_trains_at_breakfast_large_span():
+    """log_likelihood().backward() through the module at C = 48, D = 64, K = 500 (configs[3])."""
+    from action_segmentation_b200.args import HsmmArgs
+    from oracle.module_oracle import ModuleOracle
+    torch.manual_seed(0)
+    C, D, K, B, T = 48, 64, 500, 2, 700
+    m = pkg.SemiMarkovModule(HsmmArgs(sm_max_span_length=K), C, D, allow_self_transitions=True).cuda()
+    with torch.no_grad():
+        m.gaussian_means.normal_(0, 0.5)
+        m.poisson_log_rates.uniform_(2.0, 5.0)
+        m.transition_logits.normal_()
+    lab = torch.sort(torch.randint(0, C, (B, T)), dim=1)[0].cuda()
+    feats = m.gaussian_means.detach()[lab] + torch.randn(B, T, D, device="cuda")
+    lengths = torch.LongTensor([T, T - 133])
+    feats[1, T - 133:] = 0
+    ll, _ = m.log_likelihood(feats, lengths, None)
+    ll.backward()
+    params = {k: v.detach().cpu().numpy() for k, v in m.state_dict().items()}
+    r = ModuleOracle(params, K).log_likelihood(feats.cpu().numpy(), lengths.numpy())
+    assert abs(float(ll) - r["ll"]) <= 1e-5 * abs(r["ll"])
+    for k in ("gaussian_means", "transition_logits", "init_logits", "poisson_log_rates"):
+        assert rel_err(getattr(m, k).grad.cpu().numpy(), r["grads"][k]) < 1e-4, k
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE.json sizes: oracle comparisons, not only invariants
+# ---------------------------------------------------------------------------------------------
+FULL = [
+    # (name, B, Tmin, Tmax, C, K, chain)
+    ("cfg1_cfg2_T3000_C23_K20_chain", 3, 1000, 3000, 23, 20, True),
+    ("cfg0_T3000_C11_K100", 2, 1500, 3000, 11, 100, False),
+    ("cfg3_T10000_C48_K200", 2, 4000, 10000, 48, 200, False),
+    ("cfg3_T10000_C48_K500", 2, 6000, 10000, 48, 500, False),
+    ("cfg4_T2000_C64_K100", 2, 900, 2000, 64, 100, False),
+    ("cfg4_T2000_C133_K200", 2, 900, 2000, 133, 200, False),
+    ("cfg4_T2000_C16_K50", 3, 500, 2000, 16, 50, False),
+]
+
+
+@pytest.mark.parametrize("case", FULL, ids=lambda c: c[0])
+def test_full_size_vs_oracle(case):
+    """logZ 1e-5, the four count tensors 1e-4, Viterbi exact-or-tie at the frame counts BASELINE.json names -- the
+    running normaliser (f64), the linear-window block floating point and the general kernels' prefix sums all have
+    to hold up over 3 000 - 10 000 frames."""
+    name, B, Tmin, Tmax, C, K, chain = case
+    rng = np.random.default_rng(len(name) + C + K)
+    prob = random_problem(rng, B, Tmax, C, K, Tmin=Tmin, chain=chain, ends=chain, scale=2.5)
+    prob["lenp"] = O.clamp_len_table(prob["lenp"], Tmax)
+    sp = sparse_lists(prob) if chain else (None, None)
+    logz, counts, w = run_logz_and_counts(prob, sp=sp)
+    check_against_oracle(prob, logz, counts, w)
+    d = to_dev(prob)
+    spans, _, score = pkg.hsmm.viterbi_decode(d["em"], C, d["init"], d["trans"], d["lenp"], d["end"], None,
+                                              d["lengths_i32"], d["order"], trans_pred=sp[0])
+    n_exact = check_viterbi_against_oracle(prob, spans.cpu().numpy(), score.cpu().numpy())
+    assert n_exact >= B - 1
+
+
+def test_full_size_narration_f64_state_vs_oracle():
+    """configs[2] at full length: chain constraints + -1e4 narration penalties, T = 3000."""
+    rng = np.random.default_rng(5)
+    B, Tmax, C, K = 2, 3000, 23, 20
+    prob = random_problem(rng, B, Tmax, C, K, Tmin=2000, chain=True, ends=True, narration=True)
+    # one generous window per step instead of random_problem's short ones, so that a feasible path exists
+    em = rng.normal(size=(B, Tmax, C)) * 3.0
+    for b in range(B):
+        T = int(prob["lengths"][b])
+        cuts = np.sort(rng.choice(np.arange(1, T), size=C - 1, replace=False))
+        bounds = np.concatenate([[0], cuts, [T]])
+        for c in range(1, C, 2):
+            pen = np.full(Tmax, -1e4)
+            pen[max(0, bounds[c] - 40):bounds[c + 1] + 40] = 0.0
+            em[b, :, c] += pen
+    em -= em.max(axis=2, keepdims=True)
+    prob["em"] = em
+    sp = sparse_lists(prob)
+    logz, counts, w = run_logz_and_counts(prob, sp=sp, f64_state=True)
+    check_against_oracle(prob, logz, counts, w)

@@ -198,7 +198,7 @@ def test_viterbi_random_vs_oracle(shape):
 
 
 @pytest.mark.parametrize("f64_state", [False, True], ids=["f32state", "f64state"])
-@pytest.mark.parametrize("shape", SHAPES[:7] + SHAPES[10:], ids=lambda s: "B%d_T%d_C%d_K%d" % s[:4])
+@pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "B%d_T%d_C%d_K%d" % s[:4])
 def test_logz_and_counts_random_vs_oracle(shape, f64_state):
     """logZ within 1e-5 relative, expected counts within 1e-4 relative of the fp64 oracle.  With the f64-state
     kernels (HSMM_FLAG_F64_STATE, what the module selects whenever narration constraints are given) the
@@ -336,7 +336,7 @@ def test_weighted_feature_sums_tensor_core_edges(B, Tmax, D, C):
 def test_supervised_fit_golden(golden):
     """fit_supervised closed form (semimarkov_modules.py:195-256) against the reference's fitted parameters."""
     import action_segmentation_b200 as pkg
-    from tests.golden.ref_import import RefArgs
+    from action_segmentation_b200.args import HsmmArgs as RefArgs
     g = golden("supervised_fit")
     C, K = int(g["n_classes"]), int(g["max_k"])
     D = g["features"].shape[1]
@@ -371,7 +371,7 @@ def test_full_size_properties():
     """BASELINE-size batch (CrossTask shape: D=200, C=23, K=20, T up to 3000): size-independent
     invariants of the DP outputs."""
     import action_segmentation_b200 as pkg
-    from tests.golden.ref_import import RefArgs
+    from action_segmentation_b200.args import HsmmArgs as RefArgs
     torch.manual_seed(5)
     B, Tmax, D, C, K = 64, 3000, 200, 23, 20
     m = pkg.SemiMarkovModule(RefArgs(sm_max_span_length=K), C, D, allow_self_transitions=True).cuda()
@@ -610,7 +610,7 @@ def test_em_statistics_and_closed_form_update():
     class layout, and the closed-form M-step: every EM iteration must not decrease the mean log-likelihood."""
     import action_segmentation_b200 as pkg
     from oracle.module_oracle import ModuleOracle
-    from tests.golden.ref_import import RefArgs
+    from action_segmentation_b200.args import HsmmArgs as RefArgs
     torch.manual_seed(11)
     B, T, D, C, K = 12, 120, 16, 7, 20
     chain = {c: {c, c + 1} for c in range(C - 1)}

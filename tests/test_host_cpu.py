@@ -10,7 +10,7 @@ import pytest
 import torch
 
 import action_segmentation_b200 as pkg
-from tests.golden.ref_import import RefArgs
+from action_segmentation_b200.args import HsmmArgs as RefArgs
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -148,7 +148,7 @@ def test_data_stand_in_batch_contract():
 def test_em_update_closed_form_on_given_statistics():
     """M-step arithmetic (no kernels involved): normalised counts under the constraint masks, mean segment length,
     class means = wx / wsum, untouched parameters for classes without mass."""
-    from tests.golden.ref_import import RefArgs
+    from action_segmentation_b200.args import HsmmArgs as RefArgs
     C, D = 4, 3
     m = pkg.SemiMarkovModule(RefArgs(sm_max_span_length=10), C, D, allow_self_transitions=True, allowed_starts={0},
                              allowed_transitions={0: {0, 1}, 1: {1, 2}, 2: {2, 3}, 3: {3}}, allowed_ends={3})
