@@ -262,7 +262,10 @@ int hsmm_logz_forward(const float* em, int ldc, const float* init, const float* 
     p.fbeta = s.fbeta; p.fgamma = s.fgamma; p.fdelta = s.fdelta; p.logz2 = s.logz2; p.fflag = s.fflag; p.bflag = s.bflag;
     p.logz = out_logz;
     p.trans_pred = trans_pred;
-    if (use_gen(C, p.L, 1, trans_pred != nullptr, p.xp != 0))
+    // a shape whose BACKWARD pass needs the general kernels also runs its forward pass there: the general forward
+    // keeps its state in double and only rounds when it stores the planes, so the posteriors of the (double) backward
+    // pass do not inherit the float recursion's accumulated rounding over thousands of frames
+    if (use_gen(C, p.L, 1, trans_pred != nullptr, p.xp != 0) || use_gen(C, p.L, 2, trans_pred != nullptr, p.xp != 0))
         return dp_gen_launch(p, 1, reinterpret_cast<char*>(saved) + align256(saved_bytes(B, Tmax, C, p.xp != 0)), (cudaStream_t)stream);
     return dp_reg_launch(p, 1, (cudaStream_t)stream);
 }
@@ -337,6 +340,40 @@ int hsmm_feature_moments(const float* X, const int32_t* lengths, int B, int Tmax
         return HSMM_ERR_SHAPE;
     }
     return launch_moments(X, lengths, B, Tmax, D, out_sum_x, out_sum_x2, num_sms(), (cudaStream_t)stream);
+}
+
+int hsmm_upload_ragged(const float* host, float* dev, const int32_t* lengths_host, int B, int Tmax, int width, void* stream) {
+    if (!host || !dev || !lengths_host) {
+        set_error("hsmm_upload_ragged: null pointer");
+        return HSMM_ERR_ARG;
+    }
+    if (B <= 0 || Tmax <= 0 || width <= 0) {
+        set_error("hsmm_upload_ragged: bad shape B=%d Tmax=%d width=%d", B, Tmax, width);
+        return HSMM_ERR_SHAPE;
+    }
+    const size_t row = (size_t)width * sizeof(float), vid = (size_t)Tmax * row;
+    // runs of full-length videos are contiguous in both buffers: one copy per run, otherwise one per video
+    int b = 0;
+    while (b < B) {
+        int len = lengths_host[b] < 0 ? 0 : (lengths_host[b] > Tmax ? Tmax : lengths_host[b]);
+        int e = b + 1;
+        size_t bytes = (size_t)len * row;
+        if (len == Tmax) {
+            while (e < B && lengths_host[e] >= Tmax) ++e;
+            bytes = (size_t)(e - b) * vid;
+        }
+        if (bytes) {
+            cudaError_t err = cudaMemcpyAsync(reinterpret_cast<char*>(dev) + (size_t)b * vid,
+                                              reinterpret_cast<const char*>(host) + (size_t)b * vid, bytes,
+                                              cudaMemcpyHostToDevice, (cudaStream_t)stream);
+            if (err != cudaSuccess) {
+                set_error("hsmm_upload_ragged: %s", cudaGetErrorString(err));
+                return HSMM_ERR_CUDA;
+            }
+        }
+        b = e;
+    }
+    return HSMM_OK;
 }
 
 int hsmm_onehot_weights(const int32_t* labels, const int32_t* lengths, int B, int Tmax, int C, int ldc, float* weights,

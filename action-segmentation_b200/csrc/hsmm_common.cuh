@@ -19,6 +19,10 @@ extern std::atomic<uint64_t> g_launches;
 int check_launch(const char* what);
 
 // ---- device helpers -----------------------------------------------------------------------
+#ifdef HSMM_ACCURATE_MUFU  // experiment switch: libm-accurate exp2/log2 instead of the MUFU approximations
+__device__ __forceinline__ float ex2(float x) { return exp2f(x); }
+__device__ __forceinline__ float lg2(float x) { return log2f(x); }
+#else
 __device__ __forceinline__ float ex2(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -29,6 +33,7 @@ __device__ __forceinline__ float lg2(float x) {
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+#endif
 
 // Barrier over the `nwarps` warps that cooperate on one video.  One warp: __syncwarp.
 // Several warps: a named barrier (ids 1..15; id 0 is __syncthreads).

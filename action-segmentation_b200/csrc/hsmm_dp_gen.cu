@@ -65,7 +65,17 @@ __global__ void gen_transpose_kernel(const float* __restrict__ trans, int C, int
     }
 }
 
-__device__ __forceinline__ float ex2d(double x) { return ex2((float)fmax(x, -1000.0)); }
+// 2^x for a double exponent: the integer part goes into the float's exponent field exactly, only the fraction
+// (|f| <= 0.5) meets the MUFU unit -- casting the whole exponent (|x| ~ 30) to float would cost 2e-6 of accuracy
+__device__ __forceinline__ float ex2d(double x) {
+    if (!(x > -140.0)) return 0.0f;
+    x = fmin(x, 126.0);
+    const double r = rint(x);
+    const float f = ex2((float)(x - r));            // in [2^-0.5, 2^0.5]
+    const int e = (int)r;
+    if (e >= -125) return __int_as_float(__float_as_int(f) + (e << 23));
+    return f * __int_as_float((e + 127 + 24) << 23) * 5.9604644775390625e-08f;  // denormal range: scale in two steps
+}
 
 template <typename ST>
 struct GenSmem {
@@ -371,15 +381,24 @@ __global__ void __launch_bounds__(1024) dp_gen_backward_kernel(const DpParams p,
                 float Ssum = 0.0f;
                 for (int jj = 0; jj < TPC; ++jj) Ssum += sm.red_s[jj * Cp + c];
                 const double Sc = (double)w * (double)Ssum;
-                sm.cls[c] = Ssum > 0.0f ? log2((double)Ssum) - sm.aux[c] : DNEG;  // zeta[n][c]
+                sm.cls[c] = Ssum > 0.0f ? (log2((double)Ssum) - sm.aux[c]) + ss : DNEG;  // zeta[n][c] = ss[n][c] + (+)_k (q + len)
                 occ += Fnext - Snext;
                 dem[(size_t)n * ldc + c] = (float)occ;
                 Snext = Sc;
-                if (n == 0) atomicAdd(p.d_init + c, (float)Sc);
+                if (n == 0) sm.red_m[c] = Sc;
             } else if (j == 0 && c < ldc) {
                 dem[(size_t)n * ldc + c] = 0.0f;
             }
-            if (n == 0) break;
+            if (n == 0) {
+                // P(first segment has class c), normalised by its own sum (see dp_lin_backward_kernel)
+                __syncthreads();
+                if (owner) {
+                    double tot = 0.0;
+                    for (int cc = 0; cc < C; ++cc) tot += sm.red_m[cc];
+                    if (tot != 0.0) atomicAdd(p.d_init + c, (float)(sm.red_m[c] * ((double)w / tot)));
+                }
+                break;
+            }
             const double nu_n = nu_np1 - (double)p.fdelta[row0 + n];
             __syncthreads();  // zeta visible; aux free
             if (owner) sm.aux[c] = (double)fgamma[(row0 + n) * ldc + c] + nu_n - lz2;

@@ -529,7 +529,13 @@ __global__ void __launch_bounds__(128, (TM == 2 && KR <= 20) ? 4 : 1) dp_lin_bac
     if (lane == 0) p.bflag[b] = flagged ? (float)(1 + why) : 0.0f;
     if (flagged) return;
     // ---- flush the per-video counts ------------------------------------------------------------
-    if (owner) atomicAdd(p.d_init + c, S0);
+    // P(first segment has class c) is a distribution over c: normalise it by its own sum instead of by the forward
+    // pass's log Z -- after T frames the two directions' float roundings differ by ~1e-7 * sqrt(T)..T, and frame 0 is
+    // where the whole difference would show
+    {
+        const float tot = warp_sum(owner ? S0 : 0.0f);
+        if (owner && tot != 0.0f) atomicAdd(p.d_init + c, S0 * (w / tot));
+    }
     if (valid) {
 #pragma unroll
         for (int i = 0; i < KR; ++i) {

@@ -757,7 +757,21 @@ __global__ void __launch_bounds__(MAXT) dp_backward_kernel(const DpParams p) {
             if (j == 0 && c < ldc) dem[(size_t)n * ldc + c] = valid ? occ : 0.0f;
             Sprev = Sc;
             if (n == 0) {
-                if (owner) atomicAdd(p.d_init + c, Sc);
+                // P(first segment has class c) is a distribution over c: normalise it by its own sum rather than by
+                // the forward pass's log Z (after T frames the float roundings of the two directions have drifted
+                // apart, and frame 0 is where the whole difference shows; see dp_lin_backward_kernel)
+                float tot;
+                if (W == 1) {
+                    tot = warp_sum(owner ? Sc : 0.0f);
+                } else {
+                    ST* ss0 = zet_s + (n & 1) * cpad;
+                    group_sync(W, bar_id);
+                    if (j == 0) ss0[wig * CPW + cl] = valid ? (ST)Sc : (ST)0;
+                    group_sync(W, bar_id);
+                    tot = 0.0f;
+                    for (int cc = 0; cc < cpad; ++cc) tot += (float)ss0[cc];
+                }
+                if (owner && tot != 0.0f) atomicAdd(p.d_init + c, Sc * (w / tot));
                 break;
             }
             const float gm_n = dcur[f];

@@ -121,7 +121,8 @@ def viterbi_decode(em, C, init, trans, lenp, end, offset, lengths_i32, order=Non
     return spans, labels, score
 
 
-def logz_forward(em, C, init, trans, lenp, end, offset, lengths_i32, order=None, trans_pred=None, f64_state=False):
+def logz_forward(em, C, init, trans, lenp, end, offset, lengths_i32, order=None, trans_pred=None, f64_state=False,
+                 saved_bytes=None):
     """hsmm_logz_forward: returns (logz (B) float64, saved workspace).  `f64_state` (HSMM_FLAG_F64_STATE): keep the
     per-class DP state in double -- for score tensors that carry the -1e4 narration penalty."""
     _need_cuda(em, init, trans, lenp, end, offset, lengths_i32, order)
@@ -129,7 +130,8 @@ def logz_forward(em, C, init, trans, lenp, end, offset, lengths_i32, order=None,
     B, T, ldc = em.shape
     K = lenp.shape[0]
     flags = FLAG_F64_STATE if f64_state else 0
-    saved = torch.empty(lib.hsmm_logz_saved_bytes(B, T, C, K, flags), device=em.device, dtype=torch.uint8)
+    nbytes = lib.hsmm_logz_saved_bytes(B, T, C, K, flags) if saved_bytes is None else saved_bytes
+    saved = torch.empty(nbytes, device=em.device, dtype=torch.uint8)
     logz = torch.empty(B, device=em.device, dtype=torch.float64)
     _lib.check(lib.hsmm_logz_forward(_p(em), ldc, _p(init), _p(trans), _p(trans_pred), _p(lenp), _p(end), _p(offset),
                                      _p(lengths_i32), _p(order), B, T, C, K, flags, _p(logz), _p(saved), _stream()),
@@ -182,6 +184,21 @@ def feature_moments(features, lengths_i32):
     sx2 = torch.zeros(D, device=X.device, dtype=torch.float64)
     _lib.check(lib.hsmm_feature_moments(_p(X), _p(lengths_i32), B, T, D, _p(sx), _p(sx2), _stream()), "hsmm_feature_moments")
     return sx, sx2
+
+
+def upload_ragged(host, dev, lengths_host_i32):
+    """hsmm_upload_ragged: copy the live rows of a padded pinned host batch (B,T,width) into the device buffer `dev`
+    (same shape; its padding rows are left as they are) on the current stream.  Returns the bytes enqueued."""
+    lib = _lib.load()
+    if host.is_cuda or not dev.is_cuda or host.dtype != torch.float32 or dev.dtype != torch.float32:
+        raise _lib.HsmmError("upload_ragged: host must be a CPU float32 tensor and dev a CUDA float32 tensor")
+    if tuple(host.shape) != tuple(dev.shape) or not host.is_contiguous() or not dev.is_contiguous():
+        raise _lib.HsmmError("upload_ragged: host and dev must be contiguous and of the same (B, T, width) shape")
+    B, T, W = host.shape
+    lh = lengths_host_i32.to(torch.int32).contiguous()
+    _lib.check(lib.hsmm_upload_ragged(ctypes.c_void_p(host.data_ptr()), _p(dev), ctypes.c_void_p(lh.data_ptr()), B, T, W,
+                                      _stream()), "hsmm_upload_ragged")
+    return int(lh.clamp(0, T).sum()) * W * 4
 
 
 def onehot_weights(labels_i32, C, lengths_i32):

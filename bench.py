@@ -1,16 +1,21 @@
 #!/usr/bin/env python
 """Benchmark of the HSMM hot path on B200: video frames/s for emission scoring + log-semiring
-forward/backward (logZ and all expected counts) + max-plus Viterbi, on synthetic CrossTask-shaped data
-(BASELINE.json configs[1]: unsupervised HSMM, --mix_tasks --task_specific_steps
---sm_constrain_transitions: 18 tasks, 133 step classes, per-task chains of 2s+1 classes, 200-dim
-features, videos sharded over the GPUs, one all-reduce of the packed sufficient statistics per step).
+forward/backward (logZ and all expected counts) + max-plus Viterbi on synthetic data of the shapes
+BASELINE.json names.
 
-    python bench.py --gpus N --steps K --warmup W          # one rank per GPU under torchrun for N > 1
-    python bench.py --impl reference ...                   # CPU port of the reference's own algorithm
+    python bench.py --gpus N --steps K --warmup W          # driver default: configs[1]; one rank per GPU under torchrun
+    python bench.py --config {0,1,2,3,4} [--max-span K]    # the other BASELINE configs (table in DESIGN.md section 6)
+    python bench.py --impl reference ...                   # the reference's own code on the host cores (oracle/_ref)
 
-Prints ONE JSON line (rank 0).  `value`: inputs resident in HBM, library kernels only.  `e2e`: the
-public module API (`log_likelihood().backward()`, `viterbi()`), features copied from pinned host
-memory and results read back inside the timed region.
+  configs[0]  S6-shape: one task, C = 11, D = 200, K = 100, T ~ U[1000, 3000], dense transitions
+  configs[1]  U7-shape HSMM EM: 18 CrossTask-like tasks (133 steps, C = 2s+1 in 7..23), D = 200, K = 20, chain-constrained
+  configs[2]  configs[1] + the -1e4 narration penalty tensor
+  configs[3]  Breakfast-shape: C = 48, D = 64, T ~ U[500, 10000], K = 200 (--max-span 500 for the large span)
+  configs[4]  decode-only sweep: 10 000 videos, T ~ U[500, 2000], D = 200, C in {16, 64, 133} x K in {50, 100, 200}
+
+Prints ONE JSON line (rank 0).  `value`: inputs resident in HBM, library kernels only.  `e2e`: the public module
+API with HOST buffers -- the live frames of every batch are copied from pinned memory (hsmm_upload_ragged) and the
+loss, spans and labels are read back inside the timed region.
 """
 import argparse
 import json
@@ -25,7 +30,6 @@ import time
 # work queues, or streams share a queue and serialise (the default of 8 caps the step at 8 concurrent kernels)
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
-import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -36,6 +40,7 @@ if ROOT not in sys.path:
 CROSSTASK_STEPS = [6, 5, 8, 11, 6, 6, 6, 11, 8, 11, 3, 7, 5, 8, 11, 5, 9, 7]
 METRIC = "video frames/sec for HSMM fwd-bwd+Viterbi"
 UNIT = "frames/s"
+SWEEP_C, SWEEP_K = (16, 64, 133), (50, 100, 200)
 
 
 def parse():
@@ -44,23 +49,64 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--videos-per-task", type=int, default=128, help="videos of each task per step and per GPU")
-    ap.add_argument("--max-span", type=int, default=20, help="--sm_max_span_length (reference default 20)")
-    ap.add_argument("--feature-dim", type=int, default=200)
-    ap.add_argument("--tmin", type=int, default=1000)
-    ap.add_argument("--tmax", type=int, default=3000)
-    ap.add_argument("--narration", action="store_true", help="configs[2]: add the -1e4 narration penalty tensor")
+    ap.add_argument("--config", type=int, default=1, choices=[0, 1, 2, 3, 4], help="index into BASELINE.json configs")
+    ap.add_argument("--videos-per-task", type=int, default=None, help="videos of each task per step and per GPU")
+    ap.add_argument("--max-span", type=int, default=None, help="--sm_max_span_length (default: the config's)")
+    ap.add_argument("--feature-dim", type=int, default=None)
+    ap.add_argument("--tmin", type=int, default=None)
+    ap.add_argument("--tmax", type=int, default=None)
+    ap.add_argument("--narration", action="store_true", help="same as --config 2")
+    ap.add_argument("--sweep-videos", type=int, default=10000, help="configs[4]: videos per (C, K) cell and GPU")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every step from Python instead of replaying a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-sample-videos", type=int, default=5)
-    ap.add_argument("--cpu-sample-frames", type=int, default=1500)
+    ap.add_argument("--no-sustained", action="store_true")
+    ap.add_argument("--sustained-seconds", type=float, default=2.0)
     ap.add_argument("--seed", type=int, default=1234)
-    return ap.parse_args()
+    args = ap.parse_args()
+    if args.narration and args.config == 1:
+        args.config = 2
+    return args
+
+
+def config_of(args):
+    """Shape parameters of the chosen BASELINE config (command-line overrides applied)."""
+    c = args.config
+    if c == 0:
+        cfg = dict(tasks=[11], chain=False, K=100, D=200, tmin=1000, tmax=3000, V=512, narration=False)
+    elif c in (1, 2):
+        cfg = dict(tasks=[2 * s + 1 for s in CROSSTASK_STEPS], chain=True, K=20, D=200, tmin=1000, tmax=3000, V=128,
+                   narration=(c == 2))
+    elif c == 3:
+        cfg = dict(tasks=[48], chain=False, K=200, D=64, tmin=500, tmax=10000, V=256, narration=False)
+    else:
+        cfg = dict(tasks=[16], chain=False, K=50, D=200, tmin=500, tmax=2000, V=1000, narration=False)
+    for key, val in (("K", args.max_span), ("D", args.feature_dim), ("tmin", args.tmin), ("tmax", args.tmax),
+                     ("V", args.videos_per_task)):
+        if val is not None:
+            cfg[key] = val
+    return cfg
+
+
+def workload_name(args, cfg):
+    c = args.config
+    if c == 0:
+        return "configs[0] S6-shape: one task, C=11 (10 steps + background) + EOS, dense transitions, D=%d, K=%d, T~U[%d,%d], " \
+               "%d videos/GPU" % (cfg["D"], cfg["K"], cfg["tmin"], cfg["tmax"], cfg["V"])
+    if c in (1, 2):
+        return "configs[1] U7-shape HSMM EM: 18 CrossTask-like tasks (133 steps, C=2s+1 in 7..23 + EOS, chain-constrained " \
+               "transitions), D=%d, K=%d, T~U[%d,%d], %d videos/task/GPU%s" % (
+                   cfg["D"], cfg["K"], cfg["tmin"], cfg["tmax"], cfg["V"],
+                   ", narration penalty -1e4 (configs[2])" if cfg["narration"] else "")
+    if c == 3:
+        return "configs[3] Breakfast-shape: C=48 + EOS, dense transitions, D=%d, K=%d, T~U[%d,%d], %d videos/GPU" % (
+            cfg["D"], cfg["K"], cfg["tmin"], cfg["tmax"], cfg["V"])
+    return "configs[4] decode-only sweep: %d videos/GPU per cell, T~U[%d,%d], D=%d, C in %s x K in %s, dense transitions" % (
+        args.sweep_videos, cfg["tmin"], cfg["tmax"], cfg["D"], list(SWEEP_C), list(SWEEP_K))
 
 
 # ---------------------------------------------------------------------------------------------
-# synthetic CrossTask-shaped workload
+# synthetic workload
 # ---------------------------------------------------------------------------------------------
 class Task:
     pass
@@ -78,68 +124,89 @@ def chain_masks(C):
     return mask, init_mask
 
 
-def make_task(t, steps, V, D, K, tmin, tmax, narration, gen, device):
-    C = 2 * steps + 1
-    tk = Task()
-    tk.C, tk.K, tk.D, tk.V = C, K, D, V
+def make_params(tk, C, K, D, chain, gen, device):
+    """Model parameters of one class set and the score tensors the DP consumes (parameter-only work)."""
+    from action_segmentation_b200 import hsmm
+    tk.C, tk.K, tk.D, tk.chain = C, K, D, chain
     means = torch.randn(C, D, generator=gen) * 0.35
-    means[0::2] = means[0]  # merged backgrounds (--annotate_background_with_previous)
+    if chain:
+        means[0::2] = means[0]  # merged backgrounds (--annotate_background_with_previous)
     tk.means = means.to(device)
     tk.cov_diag = (torch.rand(D, generator=gen) + 0.5).to(device)
-    tmask, imask = chain_masks(C)
-    tk.trans_mask, tk.init_mask = tmask, imask
     tk.trans_logits = torch.randn(C, C, generator=gen) * 0.1
     tk.init_logits = torch.rand(C, generator=gen)
-    tk.log_rates = torch.log(torch.rand(C, generator=gen) * 8 + 4)
-    trans = torch.log_softmax(tk.trans_logits.masked_fill(tmask, -1e9), dim=0)
-    init = torch.log_softmax(tk.init_logits.masked_fill(imask, -1e9), dim=0)
+    tk.log_rates = torch.log(torch.rand(C, generator=gen) * 8 + 4) if K <= 20 else \
+        torch.log(torch.rand(C, generator=gen) * (K / 4.0) + K / 8.0)
+    if chain:
+        tmask, imask = chain_masks(C)
+        tk.trans_mask, tk.init_mask = tmask, imask
+        trans = torch.log_softmax(tk.trans_logits.masked_fill(tmask, -1e9), dim=0)
+        init = torch.log_softmax(tk.init_logits.masked_fill(imask, -1e9), dim=0)
+        tk.pred, tk.succ = hsmm.sparse_transition_lists(~tmask, torch.device(device))
+    else:
+        tk.trans_mask = tk.init_mask = None
+        trans = torch.log_softmax(tk.trans_logits, dim=0)
+        init = torch.log_softmax(tk.init_logits, dim=0)
+        tk.pred = tk.succ = None
     k = torch.arange(K, dtype=torch.float32).unsqueeze(-1)
     lenp = k * tk.log_rates.unsqueeze(0) - torch.exp(tk.log_rates).unsqueeze(0) - torch.lgamma(k + 1)
     tk.trans, tk.init, tk.lenp = trans.to(device), init.to(device), lenp.to(device)
-    end = torch.full((V, C), -1e9)
-    end[:, C - 1] = 0
-    tk.end = end.to(device)
-    tk.lengths = torch.randint(tmin, tmax + 1, (V,), generator=gen)
-    tk.lengths[0] = tmax
+    tk.class_ids = torch.arange(C + 1, device=device, dtype=torch.int32)
+    tk.eparams = hsmm.emission_params(tk.means, tk.cov_diag)  # w, bias, 1/var, row constant
+
+
+def make_task(C, cfg, gen, device, V=None, X=None, lengths=None):
+    from action_segmentation_b200 import hsmm
+    tk = Task()
+    V = V or cfg["V"]
+    tk.V = V
+    make_params(tk, C, cfg["K"], cfg["D"], cfg["chain"], gen, device)
+    D = cfg["D"]
+    if cfg["chain"]:
+        end = torch.full((V, C), -1e9)
+        end[:, C - 1] = 0
+        tk.end = end.to(device)
+    else:
+        tk.end = None
+    tk.lengths = lengths if lengths is not None else torch.randint(cfg["tmin"], cfg["tmax"] + 1, (V,), generator=gen)
+    if lengths is None:
+        tk.lengths[0] = cfg["tmax"]
     Tmax = int(tk.lengths.max())
     tk.Tmax = Tmax
-    # labels: the chain in order, random cut points
-    cuts = torch.sort((torch.rand(V, C - 1, generator=gen) * (tk.lengths[:, None] - 1)).long() + 1, dim=1)[0].to(device)
-    pos = torch.arange(Tmax, device=device).unsqueeze(0).expand(V, Tmax).contiguous()
-    labels = torch.searchsorted(cuts, pos, right=True)
-    dgen = torch.Generator(device=device).manual_seed(int(torch.randint(0, 2 ** 31, (1,), generator=gen)))
-    X = torch.randn(V, Tmax, D, device=device, generator=dgen)
-    X += tk.means[labels]
-    live = (pos < tk.lengths.to(device)[:, None])
-    X *= live.unsqueeze(-1)
-    tk.X = X.contiguous()
     tk.penalty = None
-    if narration:
-        # every step gets one window around its true span; outside it the step costs -1e4 per frame
-        pen = torch.zeros(V, Tmax, C, device=device)
-        for j in range(1, C, 2):
-            inside = (labels == j)
-            lo = torch.where(inside, pos, Tmax).min(dim=1)[0] - 40
-            hi = torch.where(inside, pos, -1).max(dim=1)[0] + 40
-            allowed = (pos >= lo[:, None]) & (pos <= hi[:, None])
-            pen[:, :, j] = (~allowed).float() * -1e4
-        tk.penalty = pen
-    from action_segmentation_b200 import hsmm
+    if X is not None:
+        tk.X = X
+    else:
+        # labels: the classes in order (cyclic when there are more segments than classes), random cut points
+        nseg = C if cfg["chain"] else max(C, 24)
+        cuts = torch.sort((torch.rand(V, nseg - 1, generator=gen) * (tk.lengths[:, None] - 1)).long() + 1, dim=1)[0].to(device)
+        pos = torch.arange(Tmax, device=device).unsqueeze(0).expand(V, Tmax).contiguous()
+        labels = torch.searchsorted(cuts, pos, right=True) % C
+        dgen = torch.Generator(device=device).manual_seed(int(torch.randint(0, 2 ** 31, (1,), generator=gen)))
+        X = torch.randn(V, Tmax, D, device=device, generator=dgen)
+        X += tk.means[labels]
+        live = (pos < tk.lengths.to(device)[:, None])
+        X *= live.unsqueeze(-1)
+        tk.X = X.contiguous()
+        if cfg["narration"]:
+            # every step gets one window around its true span; outside it the step costs -1e4 per frame
+            pen = torch.zeros(V, Tmax, C, device=device)
+            for j in range(1, C, 2):
+                inside = (labels == j)
+                lo = torch.where(inside, pos, Tmax).min(dim=1)[0] - 40
+                hi = torch.where(inside, pos, -1).max(dim=1)[0] + 40
+                allowed = (pos >= lo[:, None]) & (pos <= hi[:, None])
+                pen[:, :, j] = (~allowed).float() * -1e4
+            tk.penalty = pen
     tk.lengths_i32, tk.order = hsmm.prepare_lengths(tk.lengths, torch.device(device))
     tk.frames = int(tk.lengths.sum())
-    tk.class_ids = torch.arange(C + 1, device=device, dtype=torch.int32)
     tk.gradw = torch.full((V,), 1.0 / V, device=device)
-    tk.eparams = hsmm.emission_params(tk.means, tk.cov_diag)  # w, bias, 1/var, row constant (parameter-only work)
-    # ordering constraints leave <= 2 unmasked transitions per class: hint for the sparse-transition kernels
-    tk.pred, tk.succ = hsmm.sparse_transition_lists(~tmask, torch.device(device))
     return tk
 
 
-def make_workload(args, rank, device):
+def make_workload(args, cfg, rank, device):
     gen = torch.Generator().manual_seed(args.seed + rank)
-    tasks = [make_task(t, s, args.videos_per_task, args.feature_dim, args.max_span, args.tmin, args.tmax, args.narration,
-                       gen, device) for t, s in enumerate(CROSSTASK_STEPS)]
-    return tasks
+    return [make_task(C, cfg, gen, device) for C in cfg["tasks"]]
 
 
 def packed_layout(tasks):
@@ -152,60 +219,40 @@ def packed_layout(tasks):
     return lay, off
 
 
+def env_switches():
+    return {k: os.environ[k] for k in ("HSMM_BENCH_SKIP", "HSMM_DISABLE_LIN", "HSMM_FORCE_GENERIC") if os.environ.get(k)}
+
+
 # ---------------------------------------------------------------------------------------------
 # one step of the hot path, inputs resident in HBM, library kernels only
 # ---------------------------------------------------------------------------------------------
-def device_step(tasks, streams, packed, layout, world, reduce=True, sched=None):
+def device_step(tasks, streams, packed, layout, world, reduce=True, decode_only=False):
     """One pass of the hot path over every task's batch.  Per task: emission scoring -> {forward -> backward ->
     class-weighted feature sums} on the task's stream and, concurrently on a second stream, Viterbi (which
-    needs the emission scores only).  `sched` = "interleaved": every task's emission on its own stream;
-    "emfirst": all emissions back to back on one stream before any DP kernel (the emission kernel is a
-    persistent one-CTA-per-SM kernel and otherwise waits for whole SMs to drain)."""
+    needs the emission scores only).  `decode_only` (configs[4]): emission + Viterbi."""
     from action_segmentation_b200 import hsmm
     lib = hsmm._lib.load()
-    sched = sched or os.environ.get("HSMM_BENCH_SCHED", "interleaved")
-    skip = set(filter(None, os.environ.get("HSMM_BENCH_SKIP", "").split(",")))  # ablation only: invalid as a bench number
+    skip = set(filter(None, os.environ.get("HSMM_BENCH_SKIP", "").split(",")))  # ablation only: marked invalid in the line
     cur = torch.cuda.current_stream()
-    packed.zero_()
+    if not decode_only:
+        packed.zero_()
     fork = torch.cuda.Event()
     fork.record(cur)
-    n = len(tasks)
-    ems, em_evs = [], []
-    if sched == "emfirst":
-        s_stream = streams[2 * n]
-        s_stream.wait_event(fork)
-        with torch.cuda.stream(s_stream):
-            for tk in tasks:
-                ems.append(hsmm.emission_scores(tk.X, tk.means, tk.cov_diag, tk.penalty, tk.lengths_i32, params=tk.eparams))
-            ev = torch.cuda.Event()
-            ev.record(s_stream)
-        em_evs = [ev] * n
+    n, ns = len(tasks), len(streams)
     outs = []
     for i, tk in enumerate(tasks):
-        st, st2 = streams[i], streams[n + i]
+        st, st2 = streams[i % ns], streams[(n + i) % ns]
         st.wait_event(fork)
-        off, sizes = layout[i]
-        v = []
-        o = off
-        for m in sizes:
-            v.append(packed[o:o + m])
-            o += m
-        wx, d_trans, d_len, d_init, wsum, lz = v
-        if sched == "emfirst":
-            em, rowterm, offset = ems[i]
-            st.wait_event(em_evs[i])
-            em_ready = em_evs[i]
-        else:
-            with torch.cuda.stream(st):
-                if "em" in skip and getattr(tk, "em_cache", None) is not None:
-                    em, rowterm, offset = tk.em_cache
-                else:
-                    em, rowterm, offset = hsmm.emission_scores(tk.X, tk.means, tk.cov_diag, tk.penalty, tk.lengths_i32,
-                                                               params=tk.eparams)
-                    if "em" in skip:
-                        tk.em_cache = (em, rowterm, offset)
-                em_ready = torch.cuda.Event()
-                em_ready.record(st)
+        with torch.cuda.stream(st):
+            if "em" in skip and getattr(tk, "em_cache", None) is not None:
+                em, rowterm, offset = tk.em_cache
+            else:
+                em, rowterm, offset = hsmm.emission_scores(tk.X, tk.means, tk.cov_diag, tk.penalty, tk.lengths_i32,
+                                                           params=tk.eparams)
+                if "em" in skip:
+                    tk.em_cache = (em, rowterm, offset)
+            em_ready = torch.cuda.Event()
+            em_ready.record(st)
         st2.wait_event(em_ready)
         with torch.cuda.stream(st2):
             if "vit" in skip:
@@ -215,6 +262,14 @@ def device_step(tasks, streams, packed, layout, world, reduce=True, sched=None):
                                                            tk.order, tk.class_ids, want_labels=True, want_score=False,
                                                            trans_pred=tk.pred)
                 outs.append((spans, labels, em, offset))
+        if decode_only:
+            continue
+        off, sizes = layout[i]
+        v, o = [], off
+        for m in sizes:
+            v.append(packed[o:o + m])
+            o += m
+        wx, d_trans, d_len, d_init, wsum, lz = v
         with torch.cuda.stream(st):
             xp = tk.penalty is not None
             logz, saved = hsmm.logz_forward(em, tk.C, tk.init, tk.trans, tk.lenp, tk.end, offset, tk.lengths_i32, tk.order,
@@ -232,50 +287,71 @@ def device_step(tasks, streams, packed, layout, world, reduce=True, sched=None):
         ev = torch.cuda.Event()
         ev.record(st)
         cur.wait_event(ev)
-    if world > 1 and reduce:
+    if world > 1 and reduce and not decode_only:
         torch.distributed.all_reduce(packed)
     return outs
 
 
-def e2e_step(models, tasks, host, streams):
-    """Public API with host buffers: H2D of the step's features, loss + predictions read back."""
-    lls = []
-    preds = []
-    dev_in = []
-    # the step's inputs: every task's features (and penalties) leave pinned host memory back to back, so that the
-    # copy engine never idles while the host prepares the next call
-    for i, tk in enumerate(tasks):
-        with torch.cuda.stream(streams[i % len(streams)]):
-            feats = host[i]["features"].cuda(non_blocking=True)
-            pen = None if host[i]["penalty"] is None else host[i]["penalty"].cuda(non_blocking=True)
-            dev_in.append((feats, pen))
-    for i, (m, tk) in enumerate(zip(models, tasks)):
-        st = streams[i % len(streams)]
-        with torch.cuda.stream(st):
-            feats, pen = dev_in[i]
-            m.zero_grad()
-            ll, _ = m.log_likelihood(feats, tk.lengths, None, additional_allowed_ends_per_instance=[[] for _ in range(tk.V)],
-                                     constraints=pen)
-            (-ll).backward()
-            spans, labels = m.viterbi(feats, tk.lengths, None, additional_allowed_ends_per_instance=[[] for _ in range(tk.V)],
-                                      constraints=pen, return_labels=True, non_blocking=True)
-            h = torch.empty((), dtype=torch.float32, pin_memory=True)
-            h.copy_(ll.detach(), non_blocking=True)
-            lls.append(h)
+# ---------------------------------------------------------------------------------------------
+# end to end through the public module API, HOST buffers
+# ---------------------------------------------------------------------------------------------
+class HostBatch:
+    """Pinned host copy of one task's padded batch (what `padding_colate` hands the wrapper) and its device landing
+    buffers (zeroed once: only live rows are ever copied)."""
+
+    def __init__(self, tk):
+        self.features = tk.X.cpu().pin_memory()
+        self.penalty = None if tk.penalty is None else tk.penalty.cpu().pin_memory()
+        self.lengths_i32 = tk.lengths.to(torch.int32)
+        self.dev_features = torch.zeros_like(tk.X)
+        self.dev_penalty = None if tk.penalty is None else torch.zeros_like(tk.penalty)
+        live = int(tk.lengths.sum())
+        self.h2d_bytes = live * tk.D * 4 + (0 if tk.penalty is None else live * tk.C * 4)
+
+
+def e2e_step(models, tasks, host, streams, decode_only=False):
+    """Public API with host buffers: H2D of the step's live frames, loss + predictions read back."""
+    from action_segmentation_b200 import hsmm
+    lls, preds = [], []
+    ns = len(streams)
+    # every task's live frames leave pinned memory back to back, so that the copy engine never idles while the host
+    # prepares the next call; the kernels of task i start as soon as its own copy has landed
+    for i, (tk, hb) in enumerate(zip(tasks, host)):
+        with torch.cuda.stream(streams[i % ns]):
+            hsmm.upload_ragged(hb.features, hb.dev_features, hb.lengths_i32)
+            if hb.penalty is not None:
+                hsmm.upload_ragged(hb.penalty, hb.dev_penalty, hb.lengths_i32)
+    for i, (m, tk, hb) in enumerate(zip(models, tasks, host)):
+        with torch.cuda.stream(streams[i % ns]):
+            ends = None if tk.end is None else [[] for _ in range(tk.V)]
+            if decode_only:
+                spans, labels = m.viterbi(hb.dev_features, tk.lengths, None, additional_allowed_ends_per_instance=ends,
+                                          constraints=hb.dev_penalty, return_labels=True, non_blocking=True)
+            else:
+                m.zero_grad()
+                ll, _, spans, labels = m.log_likelihood_and_viterbi(hb.dev_features, tk.lengths, None,
+                                                                    additional_allowed_ends_per_instance=ends,
+                                                                    constraints=hb.dev_penalty, non_blocking=True)
+                (-ll).backward()
+                h = torch.empty((), dtype=torch.float32, pin_memory=True)
+                h.copy_(ll.detach(), non_blocking=True)
+                lls.append(h)
             preds.append((spans, labels))
     torch.cuda.synchronize()  # every task's loss, spans and labels are now in host memory
     return float(sum(float(h) for h in lls)), preds
 
 
-def build_models(tasks, args):
+def build_models(tasks):
     import action_segmentation_b200 as pkg
-    from action_segmentation_b200.args import HsmmArgs as RefArgs
+    from action_segmentation_b200.args import HsmmArgs
     models = []
     for tk in tasks:
         C = tk.C
-        trans = {c: ({c, c + 1} if c + 1 < C else {c}) for c in range(C)}
-        m = pkg.SemiMarkovModule(RefArgs(sm_max_span_length=args.max_span), C, tk.D, allow_self_transitions=True,
-                                 allowed_starts={0}, allowed_transitions=trans, allowed_ends={C - 1}).cuda()
+        kw = {}
+        if tk.chain:
+            trans = {c: ({c, c + 1} if c + 1 < C else {c}) for c in range(C)}
+            kw = dict(allowed_starts={0}, allowed_transitions=trans, allowed_ends={C - 1})
+        m = pkg.SemiMarkovModule(HsmmArgs(sm_max_span_length=tk.K), C, tk.D, allow_self_transitions=True, **kw).cuda()
         with torch.no_grad():
             m.gaussian_means.copy_(tk.means)
             m.gaussian_cov.copy_(torch.diag(tk.cov_diag))
@@ -286,14 +362,27 @@ def build_models(tasks, args):
     return models
 
 
+def allreduce_all_gradients(models):
+    """ONE all-reduce of every model's gradients, packed (the e2e leg of N > 1)."""
+    grads = [p.grad for m in models for p in m.parameters() if p.requires_grad and p.grad is not None]
+    if not grads:
+        return
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    torch.distributed.all_reduce(flat)
+    off = 0
+    for g in grads:
+        g.copy_(flat[off:off + g.numel()].view_as(g))
+        off += g.numel()
+
+
 # ---------------------------------------------------------------------------------------------
 # per-kernel durations (serialised on one stream, CUDA events) -> dominant kernel roofline
 # ---------------------------------------------------------------------------------------------
-def kernel_breakdown(tasks, reps=3):
+def kernel_breakdown(tasks, reps=3, decode_only=False):
     """Per-kernel device time of one step with every launch serialised on one stream (CUDA events around each
     call; best of `reps` per launch, summed over the step's launches)."""
     from action_segmentation_b200 import hsmm
-    names = ["emission", "logz_forward", "logz_backward", "weighted_feature_sums", "viterbi"]
+    names = ["emission", "viterbi"] if decode_only else ["emission", "logz_forward", "logz_backward", "weighted_feature_sums", "viterbi"]
     best = {}
     launches = {n: 0 for n in names}
 
@@ -310,15 +399,16 @@ def kernel_breakdown(tasks, reps=3):
         for i, tk in enumerate(tasks):
             em, rowterm, offset = timed(("emission", i), lambda: hsmm.emission_scores(tk.X, tk.means, tk.cov_diag, tk.penalty,
                                                                                          tk.lengths_i32, params=tk.eparams))
-            xp = tk.penalty is not None
-            logz, saved = timed(("logz_forward", i), lambda: hsmm.logz_forward(em, tk.C, tk.init, tk.trans, tk.lenp, tk.end, offset,
-                                                                               tk.lengths_i32, tk.order, trans_pred=tk.pred,
-                                                                               f64_state=xp))
-            g = torch.full((tk.V,), 1.0 / tk.V, device=em.device)
-            d = timed(("logz_backward", i), lambda: hsmm.logz_backward(em, tk.C, tk.init, tk.trans, tk.lenp, tk.end,
-                                                                       tk.lengths_i32, tk.order, g, saved, trans_succ=tk.succ,
-                                                                       f64_state=xp))
-            timed(("weighted_feature_sums", i), lambda: hsmm.weighted_feature_sums(tk.X, d[3], tk.C, tk.lengths_i32))
+            if not decode_only:
+                xp = tk.penalty is not None
+                logz, saved = timed(("logz_forward", i), lambda: hsmm.logz_forward(em, tk.C, tk.init, tk.trans, tk.lenp, tk.end,
+                                                                                   offset, tk.lengths_i32, tk.order,
+                                                                                   trans_pred=tk.pred, f64_state=xp))
+                d = timed(("logz_backward", i), lambda: hsmm.logz_backward(em, tk.C, tk.init, tk.trans, tk.lenp, tk.end,
+                                                                           tk.lengths_i32, tk.order, tk.gradw, saved,
+                                                                           trans_succ=tk.succ, f64_state=xp))
+                timed(("weighted_feature_sums", i), lambda: hsmm.weighted_feature_sums(tk.X, d[3], tk.C, tk.lengths_i32))
+                del saved, d
             timed(("viterbi", i), lambda: hsmm.viterbi_decode(em, tk.C, tk.init, tk.trans, tk.lenp, tk.end, offset,
                                                               tk.lengths_i32, tk.order, tk.class_ids, want_score=False,
                                                               trans_pred=tk.pred))
@@ -326,6 +416,20 @@ def kernel_breakdown(tasks, reps=3):
                 for n in names:
                     launches[n] += 1
     return {n: sum(v for (k, _), v in best.items() if k == n) for n in names}, launches
+
+
+def compute_ceiling(tasks, frames_per_s_per_gpu, sm_mhz, decode_only):
+    """Secondary (compute) ceiling of SURVEY.md section 8(d): C*(L + C') semiring operations per frame and pass
+    (C' = 2 for the chain-constrained transition lists, else C; Viterbi 1 pass, forward 1, backward + counts 2) against
+    the FP32 lane-operation peak 148 SMs x 128 lanes x SM clock."""
+    tot_frames = float(sum(tk.frames for tk in tasks))
+    passes = 1 if decode_only else 4
+    ops = sum(tk.frames * tk.C * ((tk.K - 1) + (2 if tk.chain else tk.C)) for tk in tasks) / tot_frames * passes
+    clock = (sm_mhz or 1965.0) * 1e6
+    peak = 148 * 128 * clock
+    return {"bound": "fp32_issue", "semiring_ops_per_frame": ops, "peak_lane_ops_per_s": peak, "sm_mhz_used": clock / 1e6,
+            "achieved_lane_ops_per_s": frames_per_s_per_gpu * ops, "frac": frames_per_s_per_gpu * ops / peak,
+            "note": "algorithmic operation count; every semiring operation costs several instructions (add, max/ex2, fma)"}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -341,7 +445,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
@@ -351,12 +455,13 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([x.strip() for x in line.split(",")])
 
-    def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.25)
-        self.proc.terminate()
-        rows = [r for r in self.rows if len(r) >= 6 and r[0].isdigit()]
+    def mark(self):
+        return len(self.rows)
+
+    def summary(self, lo=0, hi=None):
+        rows = [r for r in self.rows[max(0, lo - 1):hi] if len(r) >= 6 and r[0].isdigit()]
+        if not rows:
+            rows = [r for r in self.rows if len(r) >= 6 and r[0].isdigit()][-3:]
         if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -364,18 +469,37 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(int(r[0]) for r in rows), "sm_max_mhz": int(rows[0][1]), "reasons": reasons,
                 "samples": len(rows)}
 
+    def stop(self):
+        if self.proc is None:
+            return
+        self.proc.terminate()
+
 
 # ---------------------------------------------------------------------------------------------
-# CPU arm: the reference's own algorithm (oracle/reference_port.py) on a bounded sample
+# CPU arm: the reference's own code (oracle/_ref, imported unmodified over oracle/torch_struct_shim.py)
 # ---------------------------------------------------------------------------------------------
-def cpu_sample(args, passes=1):
-    """Bounded sample of the workload for the CPU legs: about 6 s per video and pass on 16 cores, so the number of videos
-    shrinks with the number of passes (warm-up + timed steps) to keep the whole run within a few minutes."""
+def cpu_sample(args, cfg):
+    """Bounded sample of the config's workload for the CPU legs -- the SAME sample in `cpu_baseline` and in
+    `--impl reference`.  The reference materialises (B, T, K, C+1, C+1) float32 potentials and autograd keeps
+    about three copies, so T (and for configs[3]/[4] the shape itself) is reduced where that would not fit in
+    host memory; the reduction is stated in `sample`."""
     gen = torch.Generator().manual_seed(args.seed)
-    steps = 6
-    C, D, K = 2 * steps + 1, args.feature_dim, args.max_span
-    B = max(1, min(args.cpu_sample_videos, 25 // max(1, passes)))
-    T = args.cpu_sample_frames
+    c = args.config
+    reduced = ""
+    if c == 0:
+        C, K, D, B, T = 11, cfg["K"], cfg["D"], 1, 800
+        reduced = " (T reduced from <=%d: ~20 s of CPU work per step)" % cfg["tmax"]
+    elif c in (1, 2):
+        C, K, D, B, T = 13, cfg["K"], cfg["D"], 2, 1000
+        reduced = " (one 6-step task, T reduced from <=%d: ~20 s of CPU work per step)" % cfg["tmax"]
+    elif c == 3:
+        C, K, D, B, T = 48, 60, cfg["D"], 1, 120
+        reduced = " (reduced from T<=%d, K=%d: the potentials of ONE full video are %.0f GB, and this sample already costs " \
+                  "~20 s per step)" % (cfg["tmax"], cfg["K"], cfg["tmax"] * cfg["K"] * 49 * 49 * 4 / 1e9)
+    else:
+        C, K, D, B, T = 64, 100, cfg["D"], 1, 200
+        reduced = " (one mid cell of the sweep, reduced from T<=%d: C=133/K=200 needs 29 GB per video)" % cfg["tmax"]
+    chain = cfg["chain"]
     lengths = torch.randint(max(2 * C, T // 2), T + 1, (B,), generator=gen)
     lengths[0] = T
     means = torch.randn(C, D, generator=gen) * 0.35
@@ -383,45 +507,376 @@ def cpu_sample(args, passes=1):
     pos = torch.arange(T).unsqueeze(0).expand(B, T).contiguous()
     labels = torch.searchsorted(cuts, pos, right=True)
     X = (torch.randn(B, T, D, generator=gen) + means[labels]) * (pos < lengths[:, None]).unsqueeze(-1)
-    tmask, imask = chain_masks(C)
-    return dict(X=X, lengths=lengths, means=means, cov=torch.rand(D, generator=gen) + 0.5, tmask=tmask, imask=imask,
+    pen = None
+    if cfg["narration"]:
+        pen = torch.zeros(B, T, C)
+        for j in range(1, C, 2):
+            inside = labels == j
+            lo = torch.where(inside, pos, T).min(dim=1)[0] - 40
+            hi = torch.where(inside, pos, -1).max(dim=1)[0] + 40
+            pen[:, :, j] = (~((pos >= lo[:, None]) & (pos <= hi[:, None]))).float() * -1e4
+    tmask, imask = chain_masks(C) if chain else (None, None)
+    return dict(X=X, lengths=lengths, means=means, cov=torch.rand(D, generator=gen) + 0.5, tmask=tmask, imask=imask, chain=chain,
                 trans_logits=torch.randn(C, C, generator=gen) * 0.1, init_logits=torch.rand(C, generator=gen),
-                log_rates=torch.log(torch.rand(C, generator=gen) * 8 + 4), C=C, K=K, frames=int(lengths.sum()))
+                log_rates=torch.log(torch.rand(C, generator=gen) * 8 + 4), C=C, K=K, frames=int(lengths.sum()), penalty=pen,
+                decode_only=(c == 4), reduced=reduced)
 
 
-def cpu_reference_step(s):
-    from oracle.reference_port import ReferencePort
-    rp = ReferencePort(s["means"], s["cov"], s["trans_logits"], s["init_logits"], s["log_rates"], s["K"], s["tmask"], s["imask"])
-    ends = [[s["C"] - 1] for _ in range(s["X"].shape[0])]
-    rp.train_step(s["X"], s["lengths"], allowed_ends=ends)
+def reference_module(s):
+    """The UNMODIFIED reference `SemiMarkovModule` (oracle/_ref/src/models/semimarkov/semimarkov_modules.py) with the
+    sample's parameters, or None when the reference sources are not available."""
+    from action_segmentation_b200.args import HsmmArgs
+    from tests.golden import ref_import
+    if not ref_import.reference_available():
+        return None
+    mods, _ = ref_import.load_reference()
+    C = s["C"]
+    kw = {}
+    if s["chain"]:
+        kw = dict(allowed_starts={0}, allowed_transitions={c: ({c, c + 1} if c + 1 < C else {c}) for c in range(C)},
+                  allowed_ends={C - 1})
+    m = mods.SemiMarkovModule(HsmmArgs(sm_max_span_length=s["K"]), C, s["X"].shape[2], allow_self_transitions=True, **kw)
     with torch.no_grad():
-        rp.viterbi(s["X"], s["lengths"], allowed_ends=ends)
+        m.gaussian_means.copy_(s["means"])
+        m.gaussian_cov.copy_(torch.diag(s["cov"]))
+        m.transition_logits.copy_(s["trans_logits"])
+        m.init_logits.copy_(s["init_logits"])
+        m.poisson_log_rates.copy_(s["log_rates"])
+    return m
 
 
-def run_cpu_baseline(args, steps, warmup):
+def cpu_reference_step(s, module):
+    B = s["X"].shape[0]
+    ends = [[] for _ in range(B)] if s["chain"] else None
+    if module is not None:  # the reference's own code path: log_likelihood().backward() + viterbi()
+        vc = [torch.arange(s["C"]) for _ in range(B)]  # every class is valid (the reference needs the list with allowed_ends)
+        if not s["decode_only"]:
+            module.zero_grad()
+            ll, _ = module.log_likelihood(s["X"], s["lengths"], vc, additional_allowed_ends_per_instance=ends, constraints=s["penalty"])
+            (-ll).backward()
+        with torch.no_grad():
+            module.viterbi(s["X"], s["lengths"], vc, additional_allowed_ends_per_instance=ends, constraints=s["penalty"])
+        return
+    from oracle.reference_port import ReferencePort  # builder's port of the same algorithm (only without oracle/_ref)
+    rp = ReferencePort(s["means"], s["cov"], s["trans_logits"], s["init_logits"], s["log_rates"], s["K"], s["tmask"], s["imask"])
+    pends = [[s["C"] - 1] for _ in range(B)] if s["chain"] else None
+    if not s["decode_only"]:
+        rp.train_step(s["X"], s["lengths"], constraints=s["penalty"], allowed_ends=pends)
+    with torch.no_grad():
+        rp.viterbi(s["X"], s["lengths"], constraints=s["penalty"], allowed_ends=pends)
+
+
+def run_cpu_baseline(args, cfg, steps, warmup):
     torch.set_num_threads(os.cpu_count() or 1)
-    s = cpu_sample(args, steps + warmup)
+    s = cpu_sample(args, cfg)
+    module = reference_module(s)
     for _ in range(warmup):
-        cpu_reference_step(s)
+        cpu_reference_step(s, module)
     t0 = time.perf_counter()
     for _ in range(steps):
-        cpu_reference_step(s)
+        cpu_reference_step(s, module)
     dt = (time.perf_counter() - t0) / steps
-    sample = "%d videos of one 6-step task (C=%d+EOS), T<=%d, D=%d, K=%d: %d frames/step; materialised potentials + " \
-             "sequential DP + autograd backward + argmax decode (oracle/reference_port.py)" % (
-                 s["X"].shape[0], s["C"], s["X"].shape[1], s["X"].shape[2], s["K"], s["frames"])
-    return dict(value=s["frames"] / dt, unit=UNIT, cores=torch.get_num_threads(), kind="port", sample=sample), dt
+    what = "log_likelihood().backward() + viterbi()" if not s["decode_only"] else "viterbi()"
+    sample = "%d videos, C=%d+EOS, T<=%d, D=%d, K=%d, %s transitions%s%s: %d frames/step; %s of the reference's SemiMarkovModule " \
+             "(materialised potentials, sequential DP, autograd marginals) %s" % (
+                 s["X"].shape[0], s["C"], s["X"].shape[1], s["X"].shape[2], s["K"], "chain-constrained" if s["chain"] else "dense",
+                 ", narration penalty" if s["penalty"] is not None else "", s["reduced"], s["frames"], what,
+                 "imported unmodified from oracle/_ref over oracle/torch_struct_shim.py" if module is not None
+                 else "restated in oracle/reference_port.py (oracle/_ref absent)")
+    return dict(value=s["frames"] / dt, unit=UNIT, cores=torch.get_num_threads(), kind="reference" if module is not None else "port",
+                sample=sample), dt
 
 
-def workload_name(args):
-    return "configs[1] U7-shape HSMM EM: 18 CrossTask-like tasks (133 steps, C=2s+1 in 7..23 + EOS, chain-constrained " \
-           "transitions), D=%d, K=%d, T~U[%d,%d], %d videos/task/GPU%s" % (
-               args.feature_dim, args.max_span, args.tmin, args.tmax, args.videos_per_task,
-               ", narration penalty -1e4 (configs[2])" if args.narration else "")
+# ---------------------------------------------------------------------------------------------
+def bind_near_gpu(local):
+    """Pin this rank's host threads (and hence its pinned allocations, first-touch) to the CPUs NVML reports as local to
+    its GPU: with 8 ranks on one NUMA node host->device copies collapse to ~20 GB/s per GPU."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        mine = cpus & allowed
+        if mine:
+            os.sched_setaffinity(0, mine)
+            return "%d CPUs local to GPU %d" % (len(mine), local)
+        return "GPU %d's local CPUs are outside this process's cpuset (%d CPUs allowed)" % (local, len(allowed))
+    except Exception as e:  # noqa: BLE001
+        return "unavailable (%s)" % type(e).__name__
+
+
+def measure(one_step, steps, barrier, drain=None):
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(steps):
+        one_step()
+    if drain is not None:
+        drain()  # outstanding all-reduces belong to the timed steps
+    ev1.record()
+    barrier()
+    return ev0.elapsed_time(ev1)
+
+
+def reduce_timing(ms, frames, world, device):
+    t = torch.tensor([ms, float(frames)], device=device, dtype=torch.float64)
+    if world > 1:
+        tmax = t.clone()
+        torch.distributed.all_reduce(tmax, op=torch.distributed.ReduceOp.MAX)
+        tsum = t.clone()
+        torch.distributed.all_reduce(tsum, op=torch.distributed.ReduceOp.SUM)
+        return float(tmax[0]), float(tsum[1])
+    return ms, float(frames)
+
+
+def peak_hbm():
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    if "hbm_gbs" in peaks:
+        return float(peaks["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback 6650 GB/s (B200_PROFILING.md)"
+
+
+def run_train_decode(args, cfg, rank, world, device, barrier, sampler):
+    from action_segmentation_b200 import _lib
+    tasks = make_workload(args, cfg, rank, device)
+    frames = sum(tk.frames for tk in tasks)
+    layout, total = packed_layout(tasks)
+    packed = torch.zeros(total, device=device)
+    streams = [torch.cuda.Stream() for _ in range(min(2 * len(tasks), 36) + 1)]
+    D = cfg["D"]
+
+    # ---- device-resident throughput -------------------------------------------------------------
+    # The step is ~100 library kernels on 36 streams: launched from Python it is host-bound, so after the eager
+    # warm-up it is captured ONCE into a CUDA graph (same kernels, same streams/dependencies, allocations from
+    # the graph's private pool) and the timed region replays it; the packed all-reduce follows each replay.
+    for _ in range(args.warmup):
+        device_step(tasks, streams, packed, layout, world)
+    barrier()
+    graph, launches_per_step = None, None
+    graphs, packs, comm, pending = [], [packed], None, {}
+    if not args.no_graph:
+        l_cap = _lib.launch_count()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            graph_outs = device_step(tasks, streams, packed, layout, world, reduce=False)  # noqa: F841 (kept alive)
+        launches_per_step = _lib.launch_count() - l_cap
+        graphs = [graph]
+        if world > 1:
+            # double-buffered statistics: step i's packed all-reduce runs on a side stream while step i+1's graph
+            # (which accumulates into the OTHER buffer) already computes; a buffer is reused two steps later, after
+            # its all-reduce has finished
+            packed_b = torch.zeros_like(packed)
+            graph_b = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph_b):
+                graph_outs_b = device_step(tasks, streams, packed_b, layout, world, reduce=False)  # noqa: F841
+            graphs.append(graph_b)
+            packs.append(packed_b)
+            comm = torch.cuda.Stream()
+    step_no = [0]
+
+    def one_step():
+        if graph is None:
+            device_step(tasks, streams, packed, layout, world)
+            return
+        i = step_no[0] % len(graphs)
+        step_no[0] += 1
+        cur = torch.cuda.current_stream()
+        if i in pending:
+            cur.wait_event(pending.pop(i))  # the buffer's previous all-reduce is done (it is zeroed by the graph)
+        graphs[i].replay()
+        if world > 1:
+            done = torch.cuda.Event()
+            done.record(cur)
+            comm.wait_event(done)
+            with torch.cuda.stream(comm):
+                torch.distributed.all_reduce(packs[i])
+                ev = torch.cuda.Event()
+                ev.record(comm)
+            pending[i] = ev
+
+    def drain():
+        cur = torch.cuda.current_stream()
+        for ev in pending.values():
+            cur.wait_event(ev)
+        pending.clear()
+
+    for _ in range(args.warmup):
+        one_step()
+    drain()
+    barrier()
+    mark0 = sampler.mark()
+    l0 = _lib.launch_count()
+    ms = measure(one_step, args.steps, barrier, drain)
+    launches = (_lib.launch_count() - l0) if graph is None else launches_per_step * args.steps
+    ms, frames_all = reduce_timing(ms, frames, world, device)
+    ms_per_step = ms / args.steps
+    value = frames_all / (ms_per_step * 1e-3)
+
+    # ---- sustained: the same step back to back for >= 2 s (the DP kernels are issue-bound and follow the SM clock) ----
+    sustained = None
+    if not args.no_sustained:
+        n_sus = max(args.steps, int(args.sustained_seconds * 1e3 / ms_per_step) + 1)
+        barrier()
+        m0 = sampler.mark()
+        ms_s = measure(one_step, n_sus, barrier, drain)
+        m1 = sampler.mark()
+        ms_s, _ = reduce_timing(ms_s, frames, world, device)
+        sustained = {"value": frames_all / (ms_s / n_sus * 1e-3), "unit": UNIT, "steps": n_sus, "seconds": ms_s / 1e3,
+                     "ms_per_step": ms_s / n_sus, "clocks": sampler.summary(m0, m1 + 1) if rank == 0 else None}
+    # the timed region is ~0.03 s, shorter than one nvidia-smi period: the clocks line covers the timed steps AND the
+    # sustained loop that follows them
+    clocks = sampler.summary(mark0, sampler.mark() + 1) if rank == 0 else None
+
+    # ---- per-kernel durations and the roofline of the dominant kernel ---------------------------
+    peak_gbs, peak_src = peak_hbm()
+    kms, klaunch = kernel_breakdown(tasks)
+    dom = max(kms, key=kms.get)
+    meanC = sum(tk.C * tk.frames for tk in tasks) / float(frames)
+    pen_bytes = 4.0 * meanC if cfg["narration"] else 0.0
+    bpf = (4 * D + 8 + pen_bytes) if dom == "viterbi" else (8 * D + pen_bytes)
+    achieved = frames * bpf / (kms[dom] * 1e-3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(dom) if args.config in (1, 2) else None
+    except Exception:
+        pass
+    step_bytes = frames * (8 * D + 8 + pen_bytes)
+    step_frac = step_bytes / (ms_per_step * 1e-3) / 1e9 / peak_gbs
+    comp = compute_ceiling(tasks, value / world, (clocks or {}).get("sm_mhz"), False)
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
+                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_frame": bpf,
+                "kernel_ms": {k: round(v, 3) for k, v in kms.items()}, "launches_per_step": klaunch,
+                "kernel_ms_note": "launches timed alone and serialised; in the step they overlap across streams",
+                # whole step against the same peak, per GPU (step_bytes counts this rank's frames)
+                "step_achieved_gbs": step_bytes / (ms_per_step * 1e-3) / 1e9, "step_frac": step_frac,
+                "compute_ceiling": comp, "binding": "fp32_issue" if comp["frac"] > step_frac else "hbm"}
+
+    # ---- end to end through the public API -----------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(tasks, streams, frames_all, args, world, device, barrier, False)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu, _ = run_cpu_baseline(args, cfg, 1, 1)
+
+    return {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": workload_name(args, cfg), "frames_per_step_per_gpu": frames, "videos_per_step_per_gpu":
+                   sum(tk.V for tk in tasks), "parallelism": "dp%d over videos, 1 packed all-reduce/step%s" % (
+                       world, " on a side stream, overlapping the next step (double-buffered statistics)" if world > 1 and graph is not None else ""),
+                   "launch": "eager (Python)" if graph is None else "CUDA-graph replay of the step (captured after eager warm-up)",
+                   "l2_policy": "inputs larger than L2 (%.1f GB of features per step per GPU)" % (frames * D * 4 / 1e9),
+                   "dp_variants": sorted(set("%s | %s | %s" % tuple(_lib.dp_variant(tk.C, tk.K, m, tk.chain, tk.penalty is not None)
+                                                                    for m in (0, 1, 2)) for tk in tasks))},
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "sustained": sustained, "gpu_launches": int(launches), "clocks": clocks,
+    }
+
+
+def run_e2e(tasks, streams, frames_all, args, world, device, barrier, decode_only):
+    models = build_models(tasks)
+    host = [HostBatch(tk) for tk in tasks]
+    h2d = sum(h.h2d_bytes for h in host)
+    d2h = sum(tk.V * (tk.Tmax + 1) * 8 + tk.V * tk.Tmax * 8 + 4 for tk in tasks)
+    for _ in range(max(1, min(args.warmup, 2))):
+        e2e_step(models, tasks, host, streams, decode_only)
+    barrier()
+    t0 = time.perf_counter()
+    n_e2e = max(1, min(args.steps, 3))
+    for _ in range(n_e2e):
+        e2e_step(models, tasks, host, streams, decode_only)
+        if world > 1 and not decode_only:
+            allreduce_all_gradients(models)
+    barrier()
+    dt = (time.perf_counter() - t0) / n_e2e
+    tt = torch.tensor([dt], device=device, dtype=torch.float64)
+    if world > 1:
+        torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
+    padded = sum(h.features.numel() * 4 + (0 if h.penalty is None else h.penalty.numel() * 4) for h in host)
+    return {"value": frames_all / float(tt[0]), "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
+            "ms_per_step": float(tt[0]) * 1e3, "steps": n_e2e, "h2d_gbs_achieved": h2d / float(tt[0]) / 1e9,
+            "note": "live frames only cross PCIe (hsmm_upload_ragged: %.2f of the padded %.2f GB per GPU); one emission pass "
+                    "per batch (log_likelihood_and_viterbi); one packed gradient all-reduce per step when N > 1" % (h2d / 1e9, padded / 1e9)}
+
+
+def run_sweep(args, cfg, rank, world, device, barrier, sampler):
+    """configs[4]: decode-only throughput over C x K, the same videos for every cell."""
+    from action_segmentation_b200 import _lib
+    gen = torch.Generator().manual_seed(args.seed + rank)
+    nv = args.sweep_videos
+    chunk = min(nv, cfg["V"])
+    peak_gbs, peak_src = peak_hbm()
+    D = cfg["D"]
+    # the videos: built once (features around 16 class means), shared by every cell
+    base = [make_task(16, cfg, gen, device, V=min(chunk, nv - i)) for i in range(0, nv, chunk)]
+    frames = sum(tk.frames for tk in base)
+    streams = [torch.cuda.Stream() for _ in range(min(2 * len(base), 20) + 1)]
+    cells, tot_ms, tot_frames, launches = [], 0.0, 0.0, 0
+    mark0 = sampler.mark()
+    steps = max(1, min(args.steps, 2))
+    for C in SWEEP_C:
+        for K in SWEEP_K:
+            ccfg = dict(cfg, K=K)
+            tasks = [make_task(C, ccfg, gen, device, V=b.V, X=b.X, lengths=b.lengths) for b in base]
+            for _ in range(max(1, min(args.warmup, 3))):
+                device_step(tasks, streams, None, None, world, decode_only=True)
+            barrier()
+            l0 = _lib.launch_count()
+            ms = measure(lambda: device_step(tasks, streams, None, None, world, decode_only=True), steps, barrier)
+            launches += _lib.launch_count() - l0
+            ms, frames_all = reduce_timing(ms, frames, world, device)
+            kms, _ = kernel_breakdown(tasks, reps=1, decode_only=True)
+            v = frames_all / (ms / steps * 1e-3)
+            comp = compute_ceiling(tasks, v / world, None, True)
+            hbm_frac = (v / world) * (4 * D + 8) / 1e9 / peak_gbs
+            cells.append({"C": C, "K": K, "frames_per_s": v, "ms_per_step": ms / steps, "hbm_frac": hbm_frac,
+                          "fp32_issue_frac": comp["frac"], "binding": "fp32_issue" if comp["frac"] > hbm_frac else "hbm",
+                          "viterbi_variant": _lib.dp_variant(C, K, 0), "kernel_ms": {k: round(x, 3) for k, x in kms.items()}})
+            tot_ms += ms / steps
+            tot_frames += frames_all
+            del tasks
+            torch.cuda.empty_cache()
+    clocks = sampler.summary(mark0, sampler.mark() + 1) if rank == 0 else None
+    value = tot_frames / (tot_ms * 1e-3)
+    worst = max(cells, key=lambda c: c["ms_per_step"])
+    roofline = {"bound": "hbm", "kernel": "viterbi", "achieved": (value / world) * (4 * D + 8) / 1e9, "peak": peak_gbs, "unit": "GB/s",
+                "frac": (value / world) * (4 * D + 8) / 1e9 / peak_gbs, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_frame": 4 * D + 8,
+                "note": "whole sweep (emission + Viterbi of all nine cells); the slowest cell is C=%d K=%d, bound by %s" % (
+                    worst["C"], worst["K"], worst["binding"])}
+    e2e = None
+    if not args.no_e2e:
+        # end to end on the first cell (C=16, K=50): live frames from pinned host memory, labels + spans back
+        sub = base[:4]
+        etasks = [make_task(16, dict(cfg, K=50), gen, device, V=b.V, X=b.X, lengths=b.lengths) for b in sub]
+        fr = float(sum(b.frames for b in sub)) * world
+        e2e = run_e2e(etasks, streams, fr, args, world, device, barrier, True)
+        e2e["note"] += "; cell C=16 K=50 on %d videos/GPU" % sum(b.V for b in sub)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu, _ = run_cpu_baseline(args, cfg, 1, 1)
+    return {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": args.warmup,
+        "ms_per_step": tot_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args, cfg), "frames_per_cell_per_gpu": frames, "videos_per_cell_per_gpu": nv,
+                   "parallelism": "dp%d over videos, no collective (decode)" % world,
+                   "launch": "eager (Python), %d batches of %d videos" % (len(base), chunk),
+                   "l2_policy": "inputs larger than L2 (%.1f GB of features per cell per GPU)" % (frames * D * 4 / 1e9),
+                   "step": "one step = the nine (C, K) cells once; value = frames of all cells / summed cell times"},
+        "sweep": cells, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+    }
 
 
 def main():
     args = parse()
+    cfg = config_of(args)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -429,28 +884,22 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        cb, dt = run_cpu_baseline(args, max(1, args.steps), max(0, min(args.warmup, 1)))
+        cb, dt = run_cpu_baseline(args, cfg, max(1, args.steps), max(0, min(args.warmup, 1)))
         print(json.dumps({
             "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": {"workload": workload_name(args), "sample": cb["sample"]},
+            "dtype": "f32", "data": "synthetic", "config": {"workload": workload_name(args, cfg), "sample": cb["sample"]},
             "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}))
         return
 
     assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback for the HSMM path)"
+    affinity = bind_near_gpu(local) if world > 1 else "not applied (single rank)"
     torch.cuda.set_device(local)
     device = "cuda:%d" % local
     if world > 1:
         torch.distributed.init_process_group("nccl", device_id=torch.device(device))
-    import action_segmentation_b200 as pkg
-    from action_segmentation_b200 import _lib
-
-    tasks = make_workload(args, rank, device)
-    frames = sum(tk.frames for tk in tasks)
-    layout, total = packed_layout(tasks)
-    packed = torch.zeros(total, device=device)
-    streams = [torch.cuda.Stream() for _ in range(2 * len(tasks) + 1)]
+    import action_segmentation_b200  # noqa: F401
 
     def barrier():
         torch.cuda.synchronize()
@@ -458,150 +907,22 @@ def main():
             torch.distributed.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident throughput -------------------------------------------------------------
-    # The step is ~90 library kernels on 36 streams: launched from Python it is host-bound, so after the eager
-    # warm-up it is captured ONCE into a CUDA graph (same kernels, same streams/dependencies, allocations from
-    # the graph's private pool) and the timed region replays it; the packed all-reduce follows each replay.
-    for _ in range(args.warmup):
-        device_step(tasks, streams, packed, layout, world)
-    barrier()
-    graph = None
-    launches_per_step = None
-    if not args.no_graph:
-        l_cap = _lib.launch_count()
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            graph_outs = device_step(tasks, streams, packed, layout, world, reduce=False)  # noqa: F841 (kept alive)
-        launches_per_step = _lib.launch_count() - l_cap
-
-    def one_step():
-        if graph is None:
-            device_step(tasks, streams, packed, layout, world)
-        else:
-            graph.replay()
-            if world > 1:
-                torch.distributed.all_reduce(packed)
-
-    for _ in range(args.warmup):
-        one_step()
-    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    l0 = _lib.launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for _ in range(args.steps):
-        one_step()
-    ev1.record()
-    barrier()
-    ms = ev0.elapsed_time(ev1)
-    launches = (_lib.launch_count() - l0) if graph is None else launches_per_step * args.steps
-    clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([ms, float(frames)], device=device, dtype=torch.float64)
-    if world > 1:
-        tmax = t.clone()
-        torch.distributed.all_reduce(tmax, op=torch.distributed.ReduceOp.MAX)
-        tsum = t.clone()
-        torch.distributed.all_reduce(tsum, op=torch.distributed.ReduceOp.SUM)
-        ms, frames_all = float(tmax[0]), float(tsum[1])
+    if args.config == 4:
+        result = run_sweep(args, cfg, rank, world, device, barrier, sampler)
     else:
-        frames_all = float(frames)
-    ms_per_step = ms / args.steps
-    value = frames_all / (ms_per_step * 1e-3)
-
-    # ---- per-kernel durations and the roofline of the dominant kernel ---------------------------
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
-    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    kms, klaunch = kernel_breakdown(tasks)
-    dom = max(kms, key=kms.get)
-    D = args.feature_dim
-    meanC = sum(tk.C * tk.frames for tk in tasks) / float(frames)
-    pen_bytes = 4.0 * meanC if args.narration else 0.0
-    bytes_per_frame = {"viterbi": 4 * D + 8 + pen_bytes}
-    train_bpf = 8 * D + pen_bytes
-    bpf = bytes_per_frame.get(dom, train_bpf)
-    achieved = frames * bpf / (kms[dom] * 1e-3) / 1e9
-    traffic = None
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(dom)
-    except Exception:
-        pass
-    step_bytes = frames * (8 * D + 8 + pen_bytes)
-    # secondary (compute) ceiling of the dominant kernel, SURVEY 8(d): the DP kernels are bound by FP32 issue, not HBM.
-    # Issue-slot utilisation comes from the committed ncu summaries (a profiler number, never a bench value).
-    compute = None
-    try:
-        import csv
-        names = {"logz_backward": "dp_lin_backward", "logz_forward": "dp_lin_forward", "viterbi": "dp_vit2",
-                 "emission": "emission_tc", "weighted_feature_sums": "weighted_sums"}
-        def issue_pct(path):
-            rows = list(csv.reader(open(os.path.join(ROOT, "profiles", path))))
-            col = rows[0].index("smsp__issue_active.avg.pct_of_peak_sustained_active")
-            v = [float(r[col]) for r in rows[2:] if names[dom] in r[0]]
-            return sum(v) / len(v) if v else None
-        compute = {"bound": "fp32_issue", "issue_active_pct_in_step_launch": issue_pct("r01m_ncu_bench_top_summary.csv"),
-                   "issue_active_pct_saturated_launch": issue_pct("r01d_ncu_dp_saturated_summary.csv"),
-                   "source": "profiles/r01m_ncu_bench_top_summary.csv, profiles/r01d_ncu_dp_saturated_summary.csv (ncu)"}
-    except Exception:
-        pass
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
-                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_frame": bpf,
-                "kernel_ms": {k: round(v, 3) for k, v in kms.items()}, "launches_per_step": klaunch,
-                # whole step against the same peak, per GPU (step_bytes counts this rank's frames)
-                "step_achieved_gbs": step_bytes / (ms_per_step * 1e-3) / 1e9,
-                "step_frac": step_bytes / (ms_per_step * 1e-3) / 1e9 / peak_gbs, "compute_ceiling": compute}
-
-    # ---- end to end through the public API -----------------------------------------------------
-    e2e = None
-    if not args.no_e2e:
-        models = build_models(tasks, args)
-        host = [{"features": tk.X.cpu().pin_memory(), "penalty": None if tk.penalty is None else tk.penalty.cpu().pin_memory()}
-                for tk in tasks]
-        h2d = sum(h["features"].numel() * 4 + (0 if h["penalty"] is None else h["penalty"].numel() * 4) for h in host)
-        d2h = sum(tk.V * (tk.Tmax + 1) * 8 + tk.V * tk.Tmax * 8 + 4 for tk in tasks)
-        for _ in range(max(1, min(args.warmup, 2))):
-            e2e_step(models, tasks, host, streams)
-        barrier()
-        t0 = time.perf_counter()
-        n_e2e = max(1, min(args.steps, 3))
-        for _ in range(n_e2e):
-            e2e_step(models, tasks, host, streams)
-            if world > 1:
-                from action_segmentation_b200 import distributed as hd
-                for m in models:
-                    hd.allreduce_gradients(m.parameters(), torch.zeros((), device=device))
-        barrier()
-        dt = (time.perf_counter() - t0) / n_e2e
-        tt = torch.tensor([dt], device=device, dtype=torch.float64)
-        if world > 1:
-            torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
-        e2e = {"value": frames_all / float(tt[0]), "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
-               "ms_per_step": float(tt[0]) * 1e3, "steps": n_e2e, "h2d_gbs_achieved": h2d / float(tt[0]) / 1e9}
-        del host
-
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu, _ = run_cpu_baseline(args, 1, 1)
-
+        result = run_train_decode(args, cfg, rank, world, device, barrier, sampler)
     if rank == 0:
-        out = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic",
-            "config": {"workload": workload_name(args), "frames_per_step_per_gpu": frames, "videos_per_step_per_gpu":
-                       sum(tk.V for tk in tasks), "parallelism": "dp%d over videos, 1 packed all-reduce/step" % world,
-                       "launch": "eager (Python)" if graph is None else "CUDA-graph replay of the step (captured after eager warm-up)",
-                       "l2_policy": "inputs larger than L2 (%.1f GB of features per step per GPU)" % (frames * D * 4 / 1e9),
-                       "dp_variants": sorted(set(_lib.dp_variant(tk.C, tk.K, 1, True) for tk in tasks))},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-        }
-        print(json.dumps(out))
+        sampler.stop()
+        result["config"]["host_affinity"] = affinity
+        sw = env_switches()
+        if sw:
+            result["config"]["env_switches"] = sw
+            if "HSMM_BENCH_SKIP" in sw:
+                result["invalid"] = "ablation run: HSMM_BENCH_SKIP drops kernels from the timed region"
+        print(json.dumps(result))
     if world > 1:
         torch.distributed.destroy_process_group()
 

@@ -180,6 +180,14 @@ int hsmm_gold_score(const float* em, int ldc, const float* init, const float* tr
 int hsmm_feature_moments(const float* X, const int32_t* lengths, int B, int Tmax, int D,
                          double* out_sum_x, double* out_sum_x2, void* stream);
 
+/*
+ * Host -> device copy of a zero-padded batch as `padding_colate` delivers it (models/model.py:42-63): only the live
+ * rows t < lengths[b] of every video cross PCIe (CrossTask-shaped batches are ~1/3 padding).  `host` (B,Tmax,width)
+ * should be pinned, `dev` (B,Tmax,width) is the device buffer (rows >= lengths[b] are left untouched: zero them once),
+ * `lengths_host` is a HOST array.  Asynchronous on `stream`.
+ */
+int hsmm_upload_ragged(const float* host, float* dev, const int32_t* lengths_host, int B, int Tmax, int width, void* stream);
+
 /* One-hot weights from labels: weights[b,t,c] = (labels[b,t] == c) for t < lengths[b] else 0. */
 int hsmm_onehot_weights(const int32_t* labels, const int32_t* lengths, int B, int Tmax, int C, int ldc,
                         float* weights, void* stream);

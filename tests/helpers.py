@@ -96,7 +96,7 @@ def to_dev(prob, device="cuda"):
                 lengths_i32=lengths_i32, order=order, C=C)
 
 
-def check_viterbi_against_oracle(prob, spans, score=None, tol=1e-4, em_round=True):
+def check_viterbi_against_oracle(prob, spans, score=None, tol=1e-4, em_round=True, stats=None):
     """Exact path match unless the CUDA path is a numerical near-tie: its fp64 score must be within
     tol (relative) of the oracle's best score.  `spans` (B,Tmax+1) in local ids, EOS = C."""
     em = prob["em"].astype(np.float32).astype(np.float64) if em_round else prob["em"]
@@ -105,6 +105,7 @@ def check_viterbi_against_oracle(prob, spans, score=None, tol=1e-4, em_round=Tru
     init = prob["init"].astype(np.float32).astype(np.float64)
     trans = prob["trans"].astype(np.float32).astype(np.float64)
     n_exact = 0
+    same_frames = total_frames = 0
     for b in range(B):
         T = int(prob["lengths"][b])
         end = None if prob["end"] is None else prob["end"][b]
@@ -115,10 +116,14 @@ def check_viterbi_against_oracle(prob, spans, score=None, tol=1e-4, em_round=Tru
         assert (row[T + 1:] == -1).all(), "padding positions must be -1"
         if (row == ref_row).all():
             n_exact += 1
+        same_frames += int((O.spans_to_labels(row[None, :T])[0] == O.spans_to_labels(ref_row[None, :T])[0]).sum())
+        total_frames += T
         mine = O.segments_from_spans(row, T)
         assert all(1 <= ln <= lenp.shape[0] - 1 for _, ln, _ in mine), "segment longer than K-1"
         s = O.path_score(mine, em[b, :T], init, trans, lenp, end)
         assert best - s <= tol * max(1.0, abs(best)), (b, best, s)
         if score is not None:
             assert abs(float(score[b]) - s) <= 1e-5 * max(1.0, abs(s)) + 1e-3, (b, float(score[b]), s)
+    if stats is not None:
+        stats["frame_agreement"] = same_frames / max(1, total_frames)
     return n_exact

@@ -261,8 +261,13 @@ def test_initialize_gaussian_matches_reference_formula():
 
 @needs_ref
 def test_gold_score_ragged_batch_matches_reference_module():
-    """a10 with videos of different lengths (the golden fixture has equal lengths): generative gold-path score and
-    its gradients against the reference module's `log_likelihood(spans=...)` run on the CPU."""
+    """a10 with videos of different lengths (the golden fixture has equal lengths): gold-path score and its gradients
+    against the reference module's `log_likelihood(spans=...)` run on the CPU ONE VIDEO AT A TIME.
+
+    Per video, because on a zero-padded ragged batch the reference's own number is not the model's score: `to_parts`
+    (semimarkov_modules.py:641-642) ignores `lengths`, so the label-0 padding behind a shorter video's EOS is scored as
+    extra class-0 segments, each EOS->0 edge costing -1e9 (a batch like this one gives ll ~ -1.5e9 there, and padding
+    counts leak into the class-0 gradients).  The kernel scores the live frames only; DESIGN.md lists the deviation."""
     mods, utils = ref_import.load_reference()
     torch.manual_seed(4)
     C, D, K, B, T = 5, 7, 9, 4, 40
@@ -274,7 +279,7 @@ def test_gold_score_ragged_batch_matches_reference_module():
         mine.poisson_log_rates.uniform_(0.5, 1.5)
     ref = mods.SemiMarkovModule(args, C, D, allow_self_transitions=True)
     ref.load_state_dict({k: v.cpu() for k, v in mine.state_dict().items()})
-    lengths = torch.LongTensor([40, 23, 9, 31])
+    lengths = torch.LongTensor([40, 23, 11, 31])
     labels = torch.randint(0, C, (B, 8)).repeat_interleave(5, dim=1)
     feats = torch.randn(B, T, D)
     for b in range(B):
@@ -287,9 +292,14 @@ def test_gold_score_ragged_batch_matches_reference_module():
         ref.zero_grad()
         ll, _ = mine.log_likelihood(feats.cuda(), lengths, None, spans=spans.cuda(), add_eos=True, use_mean_z=True)
         ll.backward()
-        ll_r, _ = ref.log_likelihood(feats, lengths, None, spans=spans, add_eos=True, use_mean_z=True)
-        ll_r.backward()
-        assert abs(float(ll) - float(ll_r)) <= 1e-4 * abs(float(ll_r)), (disc, float(ll), float(ll_r))
+        ll_r = 0.0
+        for b in range(B):
+            n = int(lengths[b])
+            one, _ = ref.log_likelihood(feats[b:b + 1, :n], lengths[b:b + 1], None, spans=spans[b:b + 1, :n], add_eos=True,
+                                        use_mean_z=True)
+            (one / B).backward()
+            ll_r += float(one) / B
+        assert abs(float(ll) - ll_r) <= 1e-4 * abs(ll_r), (disc, float(ll), ll_r)
         for k in ("gaussian_means", "transition_logits", "init_logits", "poisson_log_rates"):
             a, b_ = getattr(mine, k).grad.cpu().numpy(), getattr(ref, k).grad.numpy()
             assert np.abs(a - b_).max() <= 1e-4 * max(1e-12, np.abs(b_).max()), (disc, k)
@@ -345,4 +355,4 @@ def test_combined_loglik_and_viterbi_equals_separate_calls():
     assert torch.equal(spans, spans2) and torch.equal(labels, labels2)
     for k, p in m.named_parameters():
         if p.grad is not None:
-            assert torch.equal(p.grad, grads[k]), k
+            assert torch.allclose(p.grad, grads[k], rtol=1e-5, atol=1e-7), k  # atomics: summation order varies
