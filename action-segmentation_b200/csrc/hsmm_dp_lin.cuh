@@ -58,8 +58,12 @@ struct LinTracker {
 // ---------------------------------------------------------------------------------------------
 // forward (log-partition)
 // ---------------------------------------------------------------------------------------------
-template <int KR, int S, int TM>
+// XP: per-class state (beta, gamma, the window reference) and the saved planes in double, window in float -- for score
+// tensors that carry the -1e4 narration penalty (see state_t in hsmm_dp_reg.cuh): the penalty enters the reference
+// and cancels in the window shift, in double, before it meets an O(1) number.
+template <bool XP, int KR, int S, int TM>
 __global__ void __launch_bounds__(128) dp_lin_forward_kernel(const DpParams p) {
+    using ST = state_t<XP>;
     constexpr int CPW = Lay<S>::CPW;
     constexpr int CRR = Lay<S>::CRR;
     extern __shared__ __align__(16) float smem[];
@@ -134,16 +138,17 @@ __global__ void __launch_bounds__(128) dp_lin_forward_kernel(const DpParams p) {
 
     const float* em_b = p.em + (size_t)b * Tmax * ldc;
     const size_t row0 = (size_t)b * (Tmax + 1);
-    float* const fbeta = reinterpret_cast<float*>(p.fbeta);
-    float* const fgamma = reinterpret_cast<float*>(p.fgamma);
-    if (owner) fbeta[row0 * ldc + c] = init_c;
+    ST* const fbeta = reinterpret_cast<ST*>(p.fbeta);
+    ST* const fgamma = reinterpret_cast<ST*>(p.fgamma);
+    if (owner) fbeta[row0 * ldc + c] = (ST)init_c;
 
     float P[KR];
 #pragma unroll
     for (int i = 0; i < KR; ++i) P[i] = 0.0f;
-    float beta = init_c;  // beta^[n-1][c], relative to nu_n
-    float gprev = NEG;    // gamma~[n-1][c], relative to nu_{n-1}
-    float rref = 0.0f, eprev = 0.0f, gmprev = 0.0f;
+    ST beta = init_c;  // beta^[n-1][c], relative to nu_n
+    ST gprev = NEG;    // gamma~[n-1][c], relative to nu_{n-1}
+    ST rref = 0, eprev = 0;
+    float gmprev = 0.0f;
     double nu = 0.0;
     float nu4 = 0.0f;  // normaliser increments of the current group of 4 frames
     LinTracker trk;
@@ -156,8 +161,8 @@ __global__ void __launch_bounds__(128) dp_lin_forward_kernel(const DpParams p) {
 #pragma unroll
     for (int f = 0; f < F; ++f) enext[f] = (valid && f < T) ? __ldg(ep + f * ldc) : 0.0f;
     ep += F * ldc;
-    float* gout = fgamma + (row0 + 1) * ldc + c;
-    float* bout = fbeta + (row0 + 1) * ldc + c;
+    ST* gout = fgamma + (row0 + 1) * ldc + c;
+    ST* bout = fbeta + (row0 + 1) * ldc + c;
     float* dout = p.fdelta + row0 + 1;
 
 #pragma unroll 1
@@ -173,18 +178,18 @@ __global__ void __launch_bounds__(128) dp_lin_forward_kernel(const DpParams p) {
         const int n = n0 + f;
         if (n > T) break;
         const float efr = ecur[f];
-        const float e = efr * SC;
+        const ST e = (ST)efr * (ST)SC;
         nu4 += gmprev;
         // ---- phase 1: shift the window, add the entering element, sum against 2^len ----------
-        const float rho = fmaxf(gprev - gmprev, beta + ln_first);
-        const bool dead = rho < LIN_DEAD;
-        const float eo = (eprev - rho) + (rref - gmprev);
+        const ST rho = smax(gprev - (ST)gmprev, beta + (ST)ln_first);
+        const bool dead = rho < (ST)LIN_DEAD;
+        const float eo = (float)((eprev - rho) + (rref - (ST)gmprev));
         const float fac = dead ? 0.0f : ex2(fminf(eo, 100.0f));
         float carry = 0.0f;
         if (S > 1) carry = __shfl_up_sync(FULL, P[KR - 1], CPW);
 #pragma unroll
         for (int i = KR - 1; i > 0; --i) P[i] = P[i - 1] * fac;
-        P[0] = (j == 0) ? (dead ? 0.0f : ex2(fminf(beta - rho, 100.0f))) : carry * fac;
+        P[0] = (j == 0) ? (dead ? 0.0f : ex2(fminf((float)(beta - rho), 100.0f))) : carry * fac;
         rref = rho;
         eprev = e;
         // packed FMAs (FFMA2): two (class, length) elements per instruction, two independent accumulator pairs
@@ -203,9 +208,9 @@ __global__ void __launch_bounds__(128) dp_lin_forward_kernel(const DpParams p) {
         s = dead ? 1.0f : fmaxf(s, 1.0e-37f);
         const float lg = lg2(s);
         bad |= live && trk.step(-lg, lnmax, L) > LIN_RELEVANT;
-        const float gamma = valid ? (e + rho) + lg : NEG;
+        const ST gamma = valid ? (e + rho) + (ST)lg : (ST)NEG;
         gprev = gamma;
-        const float gm = warp_max_redux(owner ? gamma : NEG);
+        const float gm = warp_max_redux(owner ? (float)gamma : NEG);
         if (owner) *gout = gamma;
         gout += ldc;
         if (n == T) break;
@@ -214,20 +219,21 @@ __global__ void __launch_bounds__(128) dp_lin_forward_kernel(const DpParams p) {
         gmprev = gm;
         // ---- phase 2 (log domain): beta^[n][c2] = (+)_c1 gamma~[n][c1] + trans[c2,c1] - gm -------------
         if constexpr (TM == 2) {
-            float v[SPW];
-            float m = NEG;
+            ST v[SPW];
+            ST m = NEG;
 #pragma unroll
             for (int q = 0; q < SPW; ++q) {
-                v[q] = __shfl_sync(FULL, gamma, pidx[q]) + pval[q];
-                m = fmaxf(m, v[q]);
+                v[q] = __shfl_sync(FULL, gamma, pidx[q]) + (ST)pval[q];
+                m = smax(m, v[q]);
             }
             float s2 = 0.0f;
 #pragma unroll
-            for (int q = 0; q < SPW; ++q) s2 += ex2(v[q] - m);
-            beta = valid ? (m - gm) + lg2(s2) : NEG;
+            for (int q = 0; q < SPW; ++q) s2 += ex2((float)(v[q] - m));
+            beta = valid ? (m - (ST)gm) + (ST)lg2(s2) : (ST)NEG;
         } else {
+            // dense transitions: float state only (the XP instantiations are launched for sparse lists only)
             float* gs = gam_s + (n & 1) * CPW;
-            if (j == 0) gs[cl] = valid ? gamma : NEG;
+            if (j == 0) gs[cl] = valid ? (float)gamma : NEG;
             __syncwarp();
             float sq[2] = {0.0f, 0.0f};
 #pragma unroll
@@ -248,7 +254,7 @@ __global__ void __launch_bounds__(128) dp_lin_forward_kernel(const DpParams p) {
                     mfix = (m - gm) - trmax;
                 }
             }
-            beta = valid ? (trmax + mfix) + lg2(s2) : NEG;
+            beta = valid ? (ST)((trmax + mfix) + lg2(s2)) : (ST)NEG;
         }
         if (owner) *bout = beta;
         bout += ldc;
@@ -257,18 +263,11 @@ __global__ void __launch_bounds__(128) dp_lin_forward_kernel(const DpParams p) {
         nu4 = 0.0f;
     }
 
-    // ---- termination -------------------------------------------------------------------------
-    float* gT = gam_s + (T & 1) * CPW;
-    __syncwarp();
-    if (j == 0) gT[cl] = valid ? gprev : NEG;
-    __syncwarp();
-    float m = NEG;
-    for (int cc = lane; cc < C; cc += 32) m = fmaxf(m, gT[cc] + (endb ? endb[cc] * SC : 0.0f));
-    m = warp_max(m);
-    float sfin = 0.0f;
-    for (int cc = lane; cc < C; cc += 32) sfin += ex2(gT[cc] + (endb ? endb[cc] * SC : 0.0f) - m);
-    sfin = warp_sum(sfin);
-    const float final_v = m + lg2(sfin);
+    // ---- termination: gamma[T][c] sits in the owner lanes' registers (one warp per video, C <= 32) ---------------
+    const ST vfin = owner ? gprev + (ST)(endb ? endb[c] * SC : 0.0f) : (ST)NEG;
+    const ST m = warp_max(vfin);
+    const float sfin = warp_sum(owner ? ex2((float)(vfin - m)) : 0.0f);
+    const ST final_v = m + (ST)lg2(sfin);
     const double total = (nu + (double)final_v) * LN2;
     bad |= !(total > (double)DEGENERATE);  // degenerate or NaN: the log-domain kernel decides
     const bool flagged = __any_sync(FULL, bad);
@@ -282,8 +281,9 @@ __global__ void __launch_bounds__(128) dp_lin_forward_kernel(const DpParams p) {
 // ---------------------------------------------------------------------------------------------
 // backward (expected counts)
 // ---------------------------------------------------------------------------------------------
-template <int KR, int S, int TM>
-__global__ void __launch_bounds__(128, (TM == 2 && KR <= 20) ? 4 : 1) dp_lin_backward_kernel(const DpParams p) {
+template <bool XP, int KR, int S, int TM>
+__global__ void __launch_bounds__(128, (TM == 2 && KR <= 20 && !XP) ? 4 : 1) dp_lin_backward_kernel(const DpParams p) {
+    using ST = state_t<XP>;
     constexpr int CPW = Lay<S>::CPW;
     constexpr int CRR = Lay<S>::CRR;
     constexpr int FB = 2;  // frames per prefetch group (four streams are prefetched: register budget)
@@ -358,19 +358,19 @@ __global__ void __launch_bounds__(128, (TM == 2 && KR <= 20) ? 4 : 1) dp_lin_bac
         }
     }
     const float endc = valid ? (p.end ? p.end[(size_t)b * C + c] : 0.0f) * SC : NEG;
-    const float lzrel = (float)p.logz2[b];
+    const ST lzrel = (ST)p.logz2[b];
     const float w = p.grad[b];
     const float init_c = valid ? p.init[c] * SC : NEG;
 
     const size_t row0 = (size_t)b * (Tmax + 1);
-    const float* fg0 = reinterpret_cast<const float*>(p.fgamma) + row0 * ldc + c;
+    const ST* fg0 = reinterpret_cast<const ST*>(p.fgamma) + row0 * ldc + c;
     float* dem = p.d_em + (size_t)b * Tmax * ldc;
 
-    float eta = valid ? endc - lzrel : NEG;  // eta~[T]
-    float zprev = NEG;                       // zeta^[n+1][c]
-    float rref = 0.0f, eprev = 0.0f;
+    ST eta = valid ? (ST)endc - lzrel : (ST)NEG;  // eta~[T]
+    ST zprev = NEG;                               // zeta^[n+1][c]
+    ST rref = 0, eprev = 0;
     float occ = 0.0f, comp = 0.0f;
-    float Fprev = valid ? w * ex2(__ldg(fg0 + (size_t)T * ldc) + endc - lzrel) : 0.0f;
+    float Fprev = valid ? w * ex2((float)(__ldg(fg0 + (size_t)T * ldc) + (ST)endc - lzrel)) : 0.0f;
     float Sprev = 0.0f;
     float gm_next = 0.0f;
     float S0 = 0.0f;
@@ -381,25 +381,27 @@ __global__ void __launch_bounds__(128, (TM == 2 && KR <= 20) ? 4 : 1) dp_lin_bac
 
     // running pointers (frame n0 of the current group); the next group of F frames is in flight meanwhile
     const float* pe = p.em + (size_t)b * Tmax * ldc + (size_t)(T - 1) * ldc + c;
-    const float* pb = reinterpret_cast<const float*>(p.fbeta) + row0 * ldc + (size_t)(T - 1) * ldc + c;
-    const float* pg = fg0 + (size_t)(T - 1) * ldc;
+    const ST* pb = reinterpret_cast<const ST*>(p.fbeta) + row0 * ldc + (size_t)(T - 1) * ldc + c;
+    const ST* pg = fg0 + (size_t)(T - 1) * ldc;
     const float* pd = p.fdelta + row0 + (T - 1);
     float* pdem = dem + (size_t)(T - 1) * ldc + c;
     const bool wr_dem = (j == 0 && c < ldc);
-    float enext[FB], bnext[FB], gnext[FB], dnext[FB];
+    float enext[FB], dnext[FB];
+    ST bnext[FB], gnext[FB];
 #pragma unroll
     for (int f = 0; f < FB; ++f) {
         const int nn = T - 1 - f;
         const bool ok = valid && nn > 0;
         enext[f] = (valid && nn >= 0) ? __ldg(pe - f * ldc) : 0.0f;
-        bnext[f] = ok ? __ldg(pb - f * ldc) : 0.0f;
-        gnext[f] = ok ? __ldg(pg - f * ldc) : 0.0f;
+        bnext[f] = ok ? __ldg(pb - f * ldc) : (ST)0;
+        gnext[f] = ok ? __ldg(pg - f * ldc) : (ST)0;
         dnext[f] = (nn >= 1) ? __ldg(pd - f) : 0.0f;
     }
 
 #pragma unroll 1
     for (int n0 = T - 1; n0 >= 0; n0 -= FB) {
-        float ecurv[FB], bcurv[FB], gcurv[FB], dcurv[FB];
+        float ecurv[FB], dcurv[FB];
+        ST bcurv[FB], gcurv[FB];
 #pragma unroll
         for (int f = 0; f < FB; ++f) {
             ecurv[f] = enext[f];
@@ -416,29 +418,30 @@ __global__ void __launch_bounds__(128, (TM == 2 && KR <= 20) ? 4 : 1) dp_lin_bac
             const int nn = n0 - FB - f;
             const bool ok = valid && nn > 0;
             enext[f] = (valid && nn >= 0) ? __ldg(pe - f * ldc) : 0.0f;
-            bnext[f] = ok ? __ldg(pb - f * ldc) : 0.0f;
-            gnext[f] = ok ? __ldg(pg - f * ldc) : 0.0f;
+            bnext[f] = ok ? __ldg(pb - f * ldc) : (ST)0;
+            gnext[f] = ok ? __ldg(pg - f * ldc) : (ST)0;
             dnext[f] = (nn >= 1) ? __ldg(pd - f) : 0.0f;
         }
 #pragma unroll
         for (int f = 0; f < FB; ++f) {
         const int n = n0 - f;
         if (n < 0) break;
-        const float ecur = ecurv[f], bcur = bcurv[f], gcur = gcurv[f], gm_n = dcurv[f];
-        const float e = ecur * SC;
+        const float ecur = ecurv[f], gm_n = dcurv[f];
+        const ST bcur = bcurv[f], gcur = gcurv[f];
+        const ST e = (ST)ecur * (ST)SC;
         // ---- phase 1: zeta^[n][c] and the length counts ------------------------------------------
-        const float rho = fmaxf(zprev - gm_next, eta + ln_first);
-        const bool dead = rho < LIN_DEAD;
-        const float eo = (eprev - rho) + (rref - gm_next);
+        const ST rho = smax(zprev - (ST)gm_next, eta + (ST)ln_first);
+        const bool dead = rho < (ST)LIN_DEAD;
+        const float eo = (float)((eprev - rho) + (rref - (ST)gm_next));
         const float fac = dead ? 0.0f : ex2(fminf(eo, 100.0f));
         float carry = 0.0f;
         if (S > 1) carry = __shfl_up_sync(FULL, Q[KR - 1], CPW);
 #pragma unroll
         for (int i = KR - 1; i > 0; --i) Q[i] = Q[i - 1] * fac;
-        Q[0] = (j == 0) ? (dead ? 0.0f : ex2(fminf(eta - rho, 100.0f))) : carry * fac;
+        Q[0] = (j == 0) ? (dead ? 0.0f : ex2(fminf((float)(eta - rho), 100.0f))) : carry * fac;
         rref = rho;
         eprev = e;
-        const float betan = (n == 0) ? init_c : bcur;
+        const ST betan = (n == 0) ? (ST)init_c : bcur;
         // forward + backward exponent: masked scores (-1e9) cancel between the two directions -> double
         const double fb2 = (double)betan + (double)e + (double)rho;
         const float coef0 = valid ? w * ex2(fminf((float)fb2, 100.0f)) : 0.0f;
@@ -463,7 +466,7 @@ __global__ void __launch_bounds__(128, (TM == 2 && KR <= 20) ? 4 : 1) dp_lin_bac
         const float lg = lg2(s);
         const bool bad_trk = live && trk.step(-lg, lnmax, L) > LIN_RELEVANT;
         why |= (bad_tiny ? 2 : 0) | (bad_trk ? 4 : 0);
-        const float zeta = valid ? (e + rho) + lg : NEG;
+        const ST zeta = valid ? (e + rho) + (ST)lg : (ST)NEG;
         zprev = zeta;
         // ---- occupancy of frame n -------------------------------------------------------------
         {
@@ -481,32 +484,33 @@ __global__ void __launch_bounds__(128, (TM == 2 && KR <= 20) ? 4 : 1) dp_lin_bac
         }
         // ---- phase 2: eta~[n][c1] = (+)_c2 trans[c2,c1] + zeta^[n][c2] - gm_n; transition counts ------
         if constexpr (TM == 2) {
-            float v[SPW];
-            float m2 = NEG;
+            ST v[SPW];
+            ST m2 = NEG;
 #pragma unroll
             for (int q = 0; q < SPW; ++q) {
-                v[q] = __shfl_sync(FULL, zeta, sidx[q]) + sval[q];
-                m2 = fmaxf(m2, v[q]);
+                v[q] = __shfl_sync(FULL, zeta, sidx[q]) + (ST)sval[q];
+                m2 = smax(m2, v[q]);
             }
-            const float coef2 = valid ? w * ex2((gcur + m2) - gm_n) : 0.0f;
+            const float coef2 = valid ? w * ex2((float)((gcur + m2) - (ST)gm_n)) : 0.0f;
             float s2 = 0.0f;
 #pragma unroll
             for (int q = 0; q < SPW; ++q) {
-                const float pq = ex2(v[q] - m2);
+                const float pq = ex2((float)(v[q] - m2));
                 s2 += pq;
                 Es[q] = fmaf(pq, coef2, Es[q]);
             }
-            eta = valid ? (m2 - gm_n) + lg2(s2) : NEG;
+            eta = valid ? (m2 - (ST)gm_n) + (ST)lg2(s2) : (ST)NEG;
             Fprev = coef2 * s2;
         } else {
+            // dense transitions: float state only (the XP instantiations are launched for sparse lists only)
             float* zs = zet_s + (n & 1) * CPW;
-            if (j == 0) zs[cl] = valid ? zeta : NEG;
+            if (j == 0) zs[cl] = valid ? (float)zeta : NEG;
             __syncwarp();
             float m2 = NEG;
 #pragma unroll
             for (int i = 0; i < CRR; ++i) m2 = fmaxf(m2, zs[j * CRR + i] + tr[i]);
             m2 = slice_max<S>(m2);
-            const float coef2 = valid ? w * ex2((gcur + m2) - gm_n) : 0.0f;
+            const float coef2 = valid ? w * ex2(((float)gcur + m2) - gm_n) : 0.0f;
             float s2 = 0.0f;
 #pragma unroll
             for (int i = 0; i < CRR; ++i) {
@@ -515,7 +519,7 @@ __global__ void __launch_bounds__(128, (TM == 2 && KR <= 20) ? 4 : 1) dp_lin_bac
                 Et[i] = fmaf(pq, coef2, Et[i]);
             }
             s2 = slice_sum<S>(s2);
-            eta = valid ? (m2 - gm_n) + lg2(s2) : NEG;
+            eta = valid ? (ST)((m2 - gm_n) + lg2(s2)) : (ST)NEG;
             Fprev = coef2 * s2;
         }
         gm_next = gm_n;
@@ -565,28 +569,36 @@ __global__ void __launch_bounds__(128, (TM == 2 && KR <= 20) ? 4 : 1) dp_lin_bac
 static inline bool lin_variant(int v) { return v == 0 || v == 1 || v == 2 || v == 3 || v == 6; }
 
 static inline bool lin_eligible(const RegChoice& ch, bool xp) {
-    return !xp && ch.v >= 0 && ch.W == 1 && kVariants[ch.v].lreg && lin_variant(ch.v) && (ch.tm == 0 || ch.tm == 2);
+    // extended-precision state (narration penalties): sparse transition lists only, the two CrossTask variants
+    if (xp) return ch.v >= 0 && ch.W == 1 && (ch.v == 0 || ch.v == 1) && ch.tm == 2;
+    return ch.v >= 0 && ch.W == 1 && kVariants[ch.v].lreg && lin_variant(ch.v) && (ch.tm == 0 || ch.tm == 2);
 }
 
-template <int MODE, int KR, int S, int TM>
+template <int MODE, bool XP, int KR, int S, int TM>
 static int launch_lin_one(const DpParams& p, cudaStream_t st) {
     constexpr int VPB = 4;
     const int blocks = (p.B + VPB - 1) / VPB;
     const size_t smem = VPB * (2 * (32 / S) + 2) * sizeof(float);
     if constexpr (MODE == 1)
-        dp_lin_forward_kernel<KR, S, TM><<<blocks, VPB * 32, smem, st>>>(p);
+        dp_lin_forward_kernel<XP, KR, S, TM><<<blocks, VPB * 32, smem, st>>>(p);
     else
-        dp_lin_backward_kernel<KR, S, TM><<<blocks, VPB * 32, smem, st>>>(p);
+        dp_lin_backward_kernel<XP, KR, S, TM><<<blocks, VPB * 32, smem, st>>>(p);
     return check_launch("dp_lin kernel");
 }
 
 template <int MODE, int KR, int S>
 static int launch_lin_tm(const DpParams& p, int tm, cudaStream_t st) {
-    return tm == 2 ? launch_lin_one<MODE, KR, S, 2>(p, st) : launch_lin_one<MODE, KR, S, 0>(p, st);
+    return tm == 2 ? launch_lin_one<MODE, false, KR, S, 2>(p, st) : launch_lin_one<MODE, false, KR, S, 0>(p, st);
 }
 
 template <int MODE>
 static int launch_lin(const DpParams& p, const RegChoice& ch, cudaStream_t st) {
+    if (p.xp) {  // lin_eligible: sparse lists, variants 0 and 1
+        if (ch.v == 0) return launch_lin_one<MODE, true, 10, 2, 2>(p, st);
+        if (ch.v == 1) return launch_lin_one<MODE, true, 20, 1, 2>(p, st);
+        set_error("no extended-precision linear-window DP variant for this shape");
+        return -2;
+    }
     switch (ch.v) {
         case 0: return launch_lin_tm<MODE, 10, 2>(p, ch.tm, st);
         case 1: return launch_lin_tm<MODE, 20, 1>(p, ch.tm, st);

@@ -240,9 +240,14 @@ def device_step(tasks, streams, packed, layout, world, reduce=True, decode_only=
     fork.record(cur)
     n, ns = len(tasks), len(streams)
     outs = []
+    used, forked = [], set()
     for i, tk in enumerate(tasks):
         st, st2 = streams[i % ns], streams[(n + i) % ns]
-        st.wait_event(fork)
+        for x in (st, st2):
+            if id(x) not in forked:
+                forked.add(id(x))
+                used.append(x)
+                x.wait_event(fork)
         with torch.cuda.stream(st):
             if "em" in skip and getattr(tk, "em_cache", None) is not None:
                 em, rowterm, offset = tk.em_cache
@@ -283,7 +288,7 @@ def device_step(tasks, streams, packed, layout, world, reduce=True, decode_only=
                                                                hsmm._p(tk.lengths_i32), tk.V, tk.Tmax, tk.D, tk.C, hsmm._p(wx),
                                                                hsmm._p(wsum), hsmm._stream()), "hsmm_weighted_feature_sums")
             lz.copy_(logz.sum().float().reshape(1))
-    for st in streams:
+    for st in used:  # join only the streams that were forked off this step (a graph capture rejects anything else)
         ev = torch.cuda.Event()
         ev.record(st)
         cur.wait_event(ev)
