@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libhsmm_b200.so")
 SOURCES = ["hsmm_api.cu", "hsmm_dp_host.cu", "hsmm_dp_vit.cu", "hsmm_dp_fwd.cu", "hsmm_dp_fwd_xp.cu", "hsmm_dp_bwd.cu",
-           "hsmm_dp_bwd_xp.cu", "hsmm_dp_lin_fwd.cu", "hsmm_dp_lin_bwd.cu", "hsmm_dp_vit2.cu", "hsmm_dp_gen.cu", "hsmm_aux.cu", "hsmm_emission_tc.cu", "hsmm_wsums_tc.cu"]
+           "hsmm_dp_bwd_xp.cu", "hsmm_dp_lin_fwd.cu", "hsmm_dp_lin_bwd.cu", "hsmm_dp_vit2.cu", "hsmm_dp_gen.cu", "hsmm_dp_pair.cu", "hsmm_dp_group.cu", "hsmm_aux.cu", "hsmm_emission_tc.cu", "hsmm_wsums_tc.cu"]
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"] + os.environ.get("HSMM_EXTRA_NVCC_FLAGS", "").split()
 

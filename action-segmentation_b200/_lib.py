@@ -10,10 +10,21 @@ LIB_PATH = os.path.join(HERE, "libhsmm_b200.so")
 EXPORTS = [
     "hsmm_version", "hsmm_last_error", "hsmm_emission", "hsmm_emission_workspace_bytes", "hsmm_viterbi_workspace_bytes", "hsmm_logz_saved_bytes",
     "hsmm_viterbi", "hsmm_logz_forward", "hsmm_logz_backward", "hsmm_weighted_feature_sums", "hsmm_gold_score",
-    "hsmm_feature_moments", "hsmm_onehot_weights", "hsmm_dp_variant", "hsmm_launch_count", "hsmm_set_linear_window", "hsmm_set_generic_dp", "hsmm_upload_ragged",
+    "hsmm_feature_moments", "hsmm_onehot_weights", "hsmm_dp_variant", "hsmm_launch_count", "hsmm_set_linear_window", "hsmm_set_generic_dp", "hsmm_upload_ragged", "hsmm_dp_grouped", "hsmm_set_pair_min_videos",
 ]
 
 _lib = None
+
+
+class DpTask(ctypes.Structure):
+    """`hsmm_dp_task` of include/hsmm_b200.h (one batch of a grouped DP launch)."""
+    _p, _i = ctypes.c_void_p, ctypes.c_int
+    _fields_ = [("em", _p), ("ldc", _i), ("init", _p), ("trans", _p), ("trans_list", _p), ("lenp", _p), ("end", _p),
+                ("offset", _p), ("lengths", _p), ("order", _p), ("class_ids", _p),
+                ("B", _i), ("Tmax", _i), ("C", _i), ("K", _i), ("flags", _i),
+                ("out_spans", _p), ("out_labels", _p), ("out_score", _p), ("workspace", _p),
+                ("out_logz", _p), ("saved", _p),
+                ("grad_logz", _p), ("d_init", _p), ("d_trans", _p), ("d_len", _p), ("d_em", _p)]
 
 
 class HsmmError(RuntimeError):
@@ -56,6 +67,10 @@ def load():
     lib.hsmm_onehot_weights.argtypes = [p, p, i, i, i, i, p, p]
     lib.hsmm_upload_ragged.argtypes = [p, p, p, i, i, i, p]
     lib.hsmm_upload_ragged.restype = i
+    lib.hsmm_dp_grouped.argtypes = [i, i, ctypes.POINTER(DpTask), p]
+    lib.hsmm_dp_grouped.restype = i
+    lib.hsmm_set_pair_min_videos.argtypes = [i]
+    lib.hsmm_set_pair_min_videos.restype = i
     for name in ("hsmm_emission", "hsmm_viterbi", "hsmm_logz_forward", "hsmm_logz_backward", "hsmm_weighted_feature_sums",
                  "hsmm_gold_score", "hsmm_feature_moments", "hsmm_onehot_weights"):
         getattr(lib, name).restype = i
@@ -79,6 +94,11 @@ def dp_variant(C, K, mode, sparse=False, f64_state=False):
 def set_generic_dp(force):
     """Send every DP call to the general kernels (hsmm_set_generic_dp); returns the previous setting."""
     return bool(load().hsmm_set_generic_dp(int(bool(force))))
+
+
+def set_pair_min_videos(n):
+    """Minimum number of videos in a call for the two-videos-per-warp kernels (hsmm_set_pair_min_videos)."""
+    return int(load().hsmm_set_pair_min_videos(int(n)))
 
 
 def set_linear_window(enabled):

@@ -42,12 +42,14 @@ static int num_sms() {
 // implemented in the kernel translation units
 bool dp_reg_supported(int C, int L, int mode, bool sparse, bool xp);
 bool dp_lin_used(int C, int L, int mode, bool sparse, bool xp);
+int dp_pair_set_min_videos(int n);
 int dp_lin_set_enabled(int on);
 const char* dp_reg_name(int C, int L, int mode, bool sparse, bool xp);
 int dp_reg_launch(DpParams p, int mode, cudaStream_t st);
 size_t dp_gen_scratch_bytes(int C, int L);
 bool dp_gen_shape_ok(int C);
 int dp_gen_launch(DpParams p, int mode, void* scratch, cudaStream_t st);
+int dp_group_launch(const DpParams* ps, int n, int mode, cudaStream_t st);
 
 // HSMM_FORCE_GENERIC=1 / hsmm_set_generic_dp(1): every DP call takes the general kernels (tests, A/B runs)
 static std::atomic<int> g_force_gen{-1};
@@ -168,6 +170,7 @@ int hsmm_set_generic_dp(int force) {
 }
 
 int hsmm_set_linear_window(int enabled) { return dp_lin_set_enabled(enabled); }
+int hsmm_set_pair_min_videos(int n) { return dp_pair_set_min_videos(n); }
 
 static size_t viterbi_base_bytes(int B, int Tmax, int C) {
     // [beta / back-pointer plane][predecessor plane][normaliser increments (B, Tmax+1)][flags (B)]
@@ -296,6 +299,67 @@ int hsmm_logz_backward(const float* em, int ldc, const float* init, const float*
         return dp_gen_launch(p, 2, reinterpret_cast<char*>(const_cast<void*>(saved)) + align256(saved_bytes(B, Tmax, C, p.xp != 0)),
                              (cudaStream_t)stream);
     return dp_reg_launch(p, 2, (cudaStream_t)stream);
+}
+
+int hsmm_dp_grouped(int mode, int n, const hsmm_dp_task* tasks, void* stream) {
+    if (!tasks || n <= 0 || mode < 0 || mode > 2) {
+        set_error("hsmm_dp_grouped: bad arguments (mode=%d n=%d)", mode, n);
+        return HSMM_ERR_ARG;
+    }
+    if (n > GROUP_MAX) {
+        set_error("hsmm_dp_grouped: at most %d tasks per call (got %d)", GROUP_MAX, n);
+        return HSMM_ERR_SHAPE;
+    }
+    static thread_local DpParams ps[GROUP_MAX];
+    for (int i = 0; i < n; ++i) {
+        const hsmm_dp_task& t = tasks[i];
+        if (!t.em || !t.init || !t.trans || !t.trans_list || !t.lenp || !t.lengths) {
+            set_error("hsmm_dp_grouped: task %d: null pointer", i);
+            return HSMM_ERR_ARG;
+        }
+        int rc = check_dims("hsmm_dp_grouped", t.B, t.Tmax, t.C, t.K, t.ldc);
+        if (rc) return rc;
+        if (t.ldc != (t.C + 3) / 4 * 4 || t.flags != tasks[0].flags) {
+            set_error("hsmm_dp_grouped: task %d: ldc must be C rounded up to 4 and flags must agree across the group", i);
+            return HSMM_ERR_SHAPE;
+        }
+        DpParams& p = ps[i];
+        memset(&p, 0, sizeof(p));
+        p.em = t.em; p.init = t.init; p.trans = t.trans; p.lenp = t.lenp; p.end = t.end; p.offset = t.offset;
+        p.lengths = t.lengths; p.order = t.order; p.B = t.B; p.Tmax = t.Tmax; p.C = t.C; p.L = t.K - 1; p.ldc = t.ldc;
+        if (mode == 0) {
+            if (!t.out_spans || !t.workspace) {
+                set_error("hsmm_dp_grouped: task %d: Viterbi needs out_spans and workspace", i);
+                return HSMM_ERR_ARG;
+            }
+            p.bp = reinterpret_cast<uint32_t*>(t.workspace); p.class_ids = t.class_ids; p.spans = t.out_spans; p.labels = t.out_labels;
+            p.vbeta = reinterpret_cast<float*>(t.workspace);
+            p.vpred = reinterpret_cast<uint32_t*>(t.workspace) + plane_elems(t.B, t.Tmax, t.C);
+            p.vdelta = reinterpret_cast<float*>(p.vpred + plane_elems(t.B, t.Tmax, t.C));
+            p.vflag = p.vdelta + (size_t)t.B * (t.Tmax + 1);
+            p.score = t.out_score; p.trans_pred = t.trans_list;
+        } else {
+            if (!t.saved || (mode == 1 && !t.out_logz) ||
+                (mode == 2 && (!t.grad_logz || !t.d_init || !t.d_trans || !t.d_len || !t.d_em))) {
+                set_error("hsmm_dp_grouped: task %d: missing buffer for mode %d", i, mode);
+                return HSMM_ERR_ARG;
+            }
+            p.xp = (t.flags & HSMM_FLAG_F64_STATE) ? 1 : 0;
+            Saved sv = carve(t.saved, t.B, t.Tmax, t.C, p.xp != 0);
+            p.fbeta = sv.fbeta; p.fgamma = sv.fgamma; p.fdelta = sv.fdelta; p.logz2 = sv.logz2; p.fflag = sv.fflag; p.bflag = sv.bflag;
+            if (mode == 1) {
+                p.logz = t.out_logz; p.trans_pred = t.trans_list;
+            } else {
+                p.trans_succ = t.trans_list; p.grad = t.grad_logz;
+                p.d_init = t.d_init; p.d_trans = t.d_trans; p.d_len = t.d_len; p.d_em = t.d_em;
+            }
+        }
+    }
+    if (force_gen()) {
+        set_error("hsmm_dp_grouped: not available while the general kernels are forced (hsmm_set_generic_dp)");
+        return HSMM_ERR_SHAPE;
+    }
+    return dp_group_launch(ps, n, mode, (cudaStream_t)stream);
 }
 
 int hsmm_weighted_feature_sums(const float* X, const float* weights, int ldc, const int32_t* lengths, int B, int Tmax, int D,

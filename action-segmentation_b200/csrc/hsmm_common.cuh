@@ -199,4 +199,20 @@ struct DpParams {
     float* d_em;     // (B, Tmax, ldc)
 };
 
+// ---- grouped launches: one kernel over the batches of several tasks (class sets) ------------------
+// The parameter blocks travel as ONE kernel argument (by value, a few KB: works under CUDA-graph capture and needs no
+// device allocation); CTA `blockIdx.x` belongs to task t with first[t] <= blockIdx.x < first[t+1].
+constexpr int GROUP_MAX = 32;
+struct DpGroup {
+    int n;
+    int first[GROUP_MAX + 1];
+    DpParams t[GROUP_MAX];
+};
+__device__ __forceinline__ int group_find(const DpGroup& g, int bid, int& local) {
+    int t = 0;
+    while (t + 1 < g.n && bid >= g.first[t + 1]) ++t;
+    local = bid - g.first[t];
+    return t;
+}
+
 }  // namespace hsmm

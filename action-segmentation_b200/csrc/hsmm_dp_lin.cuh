@@ -62,7 +62,7 @@ struct LinTracker {
 // tensors that carry the -1e4 narration penalty (see state_t in hsmm_dp_reg.cuh): the penalty enters the reference
 // and cancels in the window shift, in double, before it meets an O(1) number.
 template <bool XP, int KR, int S, int TM>
-__global__ void __launch_bounds__(128) dp_lin_forward_kernel(const DpParams p) {
+__device__ __forceinline__ void dp_lin_forward_kernel_body(const DpParams& p, const int bid) {
     using ST = state_t<XP>;
     constexpr int CPW = Lay<S>::CPW;
     constexpr int CRR = Lay<S>::CRR;
@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(128) dp_lin_forward_kernel(const DpParams p) {
     const bool valid = c < C;
     const bool owner = valid && j == 0;
 
-    const int vidx = blockIdx.x * (blockDim.x >> 5) + warp;
+    const int vidx = bid * (blockDim.x >> 5) + warp;
     if (vidx >= p.B) return;
     const int b = p.order ? p.order[vidx] : vidx;
     const int T = p.lengths[b];
@@ -278,11 +278,22 @@ __global__ void __launch_bounds__(128) dp_lin_forward_kernel(const DpParams p) {
     }
 }
 
+template <bool XP, int KR, int S, int TM>
+__global__ void __launch_bounds__(128, (!XP && KR <= 20 && TM == 2) ? 5 : 1) dp_lin_forward_kernel(const DpParams p) {
+    dp_lin_forward_kernel_body<XP, KR, S, TM>(p, blockIdx.x);
+}
+template <bool XP, int KR, int S, int TM>
+__global__ void __launch_bounds__(128, (!XP && KR <= 20 && TM == 2) ? 5 : 1) dp_lin_forward_kernel_grouped(const __grid_constant__ DpGroup g) {
+    int local;
+    const int t = group_find(g, blockIdx.x, local);
+    dp_lin_forward_kernel_body<XP, KR, S, TM>(g.t[t], local);
+}
+
 // ---------------------------------------------------------------------------------------------
 // backward (expected counts)
 // ---------------------------------------------------------------------------------------------
 template <bool XP, int KR, int S, int TM>
-__global__ void __launch_bounds__(128, (TM == 2 && KR <= 20 && !XP) ? 4 : 1) dp_lin_backward_kernel(const DpParams p) {
+__device__ __forceinline__ void dp_lin_backward_kernel_body(const DpParams& p, const int bid) {
     using ST = state_t<XP>;
     constexpr int CPW = Lay<S>::CPW;
     constexpr int CRR = Lay<S>::CRR;
@@ -298,7 +309,7 @@ __global__ void __launch_bounds__(128, (TM == 2 && KR <= 20 && !XP) ? 4 : 1) dp_
     const bool valid = c < C;
     const bool owner = valid && j == 0;
 
-    const int vidx = blockIdx.x * (blockDim.x >> 5) + warp;
+    const int vidx = bid * (blockDim.x >> 5) + warp;
     if (vidx >= p.B) return;
     const int b = p.order ? p.order[vidx] : vidx;
     const int T = p.lengths[b];
@@ -560,6 +571,17 @@ __global__ void __launch_bounds__(128, (TM == 2 && KR <= 20 && !XP) ? 4 : 1) dp_
             }
         }
     }
+}
+
+template <bool XP, int KR, int S, int TM>
+__global__ void __launch_bounds__(128, (TM == 2 && KR <= 20 && !XP) ? 4 : 1) dp_lin_backward_kernel(const DpParams p) {
+    dp_lin_backward_kernel_body<XP, KR, S, TM>(p, blockIdx.x);
+}
+template <bool XP, int KR, int S, int TM>
+__global__ void __launch_bounds__(128, (TM == 2 && KR <= 20 && !XP) ? 4 : 1) dp_lin_backward_kernel_grouped(const __grid_constant__ DpGroup g) {
+    int local;
+    const int t = group_find(g, blockIdx.x, local);
+    dp_lin_backward_kernel_body<XP, KR, S, TM>(g.t[t], local);
 }
 
 // ---------------------------------------------------------------------------------------------

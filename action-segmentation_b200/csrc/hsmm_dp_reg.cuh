@@ -81,7 +81,7 @@ __host__ __device__ inline int ld_trans(int W, int S) {
 // forward: Viterbi (VIT) or log-partition (FWD)
 // ---------------------------------------------------------------------------------------------
 template <bool VIT, bool XP, int KR, int S, int TM, bool LREG, int MAXT>
-__global__ void __launch_bounds__(MAXT) dp_forward_kernel(const DpParams p) {
+__device__ __forceinline__ void dp_forward_kernel_body(const DpParams& p, const int bid) {
     static_assert(!(VIT && XP), "extended-precision state is a log-semiring option");
     using ST = state_t<XP>;
     constexpr int CPW = Lay<S>::CPW;
@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(MAXT) dp_forward_kernel(const DpParams p) {
     }
     if constexpr (TM == 1 || !LREG) __syncthreads();
 
-    const int vidx = blockIdx.x * p.VPB + slot;
+    const int vidx = bid * p.VPB + slot;
     if (vidx >= p.B) return;
     const int b = p.order ? p.order[vidx] : vidx;
     const int T = p.lengths[b];
@@ -527,11 +527,22 @@ __global__ void __launch_bounds__(MAXT) dp_forward_kernel(const DpParams p) {
 #undef LN
 }
 
+template <bool VIT, bool XP, int KR, int S, int TM, bool LREG, int MAXT>
+__global__ void __launch_bounds__(MAXT) dp_forward_kernel(const DpParams p) {
+    dp_forward_kernel_body<VIT, XP, KR, S, TM, LREG, MAXT>(p, blockIdx.x);
+}
+template <bool VIT, bool XP, int KR, int S, int TM, bool LREG, int MAXT>
+__global__ void __launch_bounds__(MAXT) dp_forward_kernel_grouped(const __grid_constant__ DpGroup g) {
+    int local;
+    const int t = group_find(g, blockIdx.x, local);
+    dp_forward_kernel_body<VIT, XP, KR, S, TM, LREG, MAXT>(g.t[t], local);
+}
+
 // ---------------------------------------------------------------------------------------------
 // backward: expected counts
 // ---------------------------------------------------------------------------------------------
 template <bool XP, int KR, int S, int TM, bool LREG, int MAXT>
-__global__ void __launch_bounds__(MAXT) dp_backward_kernel(const DpParams p) {
+__device__ __forceinline__ void dp_backward_kernel_body(const DpParams& p, const int bid) {
     using ST = state_t<XP>;
     constexpr int CPW = Lay<S>::CPW;
     constexpr int CRR = Lay<S>::CRR;
@@ -583,7 +594,7 @@ __global__ void __launch_bounds__(MAXT) dp_backward_kernel(const DpParams p) {
     }
     __syncthreads();
 
-    const int vidx = blockIdx.x * p.VPB + slot;
+    const int vidx = bid * p.VPB + slot;
     if (vidx >= p.B) return;
     const int b = p.order ? p.order[vidx] : vidx;
     const int T = p.lengths[b];
@@ -873,6 +884,17 @@ __global__ void __launch_bounds__(MAXT) dp_backward_kernel(const DpParams p) {
         }
     }
 #undef LN
+}
+
+template <bool XP, int KR, int S, int TM, bool LREG, int MAXT>
+__global__ void __launch_bounds__(MAXT) dp_backward_kernel(const DpParams p) {
+    dp_backward_kernel_body<XP, KR, S, TM, LREG, MAXT>(p, blockIdx.x);
+}
+template <bool XP, int KR, int S, int TM, bool LREG, int MAXT>
+__global__ void __launch_bounds__(MAXT) dp_backward_kernel_grouped(const __grid_constant__ DpGroup g) {
+    int local;
+    const int t = group_find(g, blockIdx.x, local);
+    dp_backward_kernel_body<XP, KR, S, TM, LREG, MAXT>(g.t[t], local);
 }
 
 // ---------------------------------------------------------------------------------------------

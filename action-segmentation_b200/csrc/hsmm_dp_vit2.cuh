@@ -17,7 +17,7 @@
 namespace hsmm {
 
 template <int KR, int S, int TM>
-__global__ void __launch_bounds__(128) dp_vit2_kernel(const DpParams p) {
+__device__ __forceinline__ void dp_vit2_kernel_body(const DpParams& p, const int bid) {
     constexpr int CPW = Lay<S>::CPW;
     constexpr int CRR = Lay<S>::CRR;
     extern __shared__ __align__(16) float smem[];
@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(128) dp_vit2_kernel(const DpParams p) {
     const bool valid = c < C;
     const bool owner = valid && j == 0;
 
-    const int vidx = blockIdx.x * (blockDim.x >> 5) + warp;
+    const int vidx = bid * (blockDim.x >> 5) + warp;
     if (vidx >= p.B) return;
     const int b = p.order ? p.order[vidx] : vidx;
     const int T = p.lengths[b];
@@ -219,6 +219,17 @@ __global__ void __launch_bounds__(128) dp_vit2_kernel(const DpParams p) {
         cc = (c1 < C) ? c1 : C - 1;
         n = start;
     }
+}
+
+template <int KR, int S, int TM>
+__global__ void __launch_bounds__(128) dp_vit2_kernel(const DpParams p) {
+    dp_vit2_kernel_body<KR, S, TM>(p, blockIdx.x);
+}
+template <int KR, int S, int TM>
+__global__ void __launch_bounds__(128) dp_vit2_kernel_grouped(const __grid_constant__ DpGroup g) {
+    int local;
+    const int t = group_find(g, blockIdx.x, local);
+    dp_vit2_kernel_body<KR, S, TM>(g.t[t], local);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -140,7 +140,7 @@ def logz_forward(em, C, init, trans, lenp, end, offset, lengths_i32, order=None,
 
 
 def logz_backward(em, C, init, trans, lenp, end, lengths_i32, order, grad_logz, saved, out=None, trans_succ=None,
-                  f64_state=False):
+                  f64_state=False, d_em=None):
     """hsmm_logz_backward: returns (d_init (C), d_trans (C,C), d_len (K,C), d_em (B,T,ldc)).
     `out` may carry pre-allocated (zeroed) d_init/d_trans/d_len views of a packed gradient buffer."""
     lib = _lib.load()
@@ -153,12 +153,71 @@ def logz_backward(em, C, init, trans, lenp, end, lengths_i32, order, grad_logz, 
         d_len = torch.zeros(K, C, device=dev)
     else:
         d_init, d_trans, d_len = out
-    d_em = torch.empty(B, T, ldc, device=dev, dtype=torch.float32)
+    if d_em is None:
+        d_em = torch.empty(B, T, ldc, device=dev, dtype=torch.float32)
     g = _f32(grad_logz)
     _lib.check(lib.hsmm_logz_backward(_p(em), ldc, _p(init), _p(trans), _p(trans_succ), _p(lenp), _p(end), _p(lengths_i32),
                                       _p(order), _p(g), B, T, C, K, FLAG_F64_STATE if f64_state else 0, _p(saved), _p(d_init),
                                       _p(d_trans), _p(d_len), _p(d_em), _stream()), "hsmm_logz_backward")
     return d_init, d_trans, d_len, d_em
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def grouped_dp(mode, batches):
+    """hsmm_dp_grouped: the Viterbi (mode 0) / forward (1) / backward (2) pass of several task-homogeneous batches in ONE
+    launch per kernel family.  `batches`: list of dicts with the per-batch tensors of the single-batch entry points
+    (em, C, init, trans, lenp, end, offset, lengths_i32, order, trans_list [, class_ids, want_labels, f64_state, grad,
+    saved, out=(d_init, d_trans, d_len), d_em]).  Returns a list of per-batch results shaped like the single-batch
+    functions': mode 0 (spans, labels, None), mode 1 (logz, saved), mode 2 (d_init, d_trans, d_len, d_em)."""
+    lib = _lib.load()
+    n = len(batches)
+    arr = (_lib.DpTask * n)()
+    keep, results = [], []
+    for i, bt in enumerate(batches):
+        em = bt["em"]
+        B, T, ldc = em.shape
+        C = bt["C"]
+        init, trans, lenp, end = _f32(bt["init"]), _f32(bt["trans"]), _f32(bt["lenp"]), _f32(bt.get("end"))
+        K = lenp.shape[0]
+        flags = FLAG_F64_STATE if bt.get("f64_state") else 0
+        t = arr[i]
+        t.em, t.ldc, t.init, t.trans, t.trans_list, t.lenp, t.end = _ptr(em), ldc, _ptr(init), _ptr(trans), _ptr(bt["trans_list"]), \
+            _ptr(lenp), _ptr(end)
+        t.offset, t.lengths, t.order, t.class_ids = _ptr(bt.get("offset")), _ptr(bt["lengths_i32"]), _ptr(bt.get("order")), \
+            _ptr(bt.get("class_ids"))
+        t.B, t.Tmax, t.C, t.K, t.flags = B, T, C, K, flags
+        keep.append((init, trans, lenp, end))
+        dev = em.device
+        if mode == 0:
+            ws = torch.empty(lib.hsmm_viterbi_workspace_bytes(B, T, C, K), device=dev, dtype=torch.uint8)
+            spans = torch.empty(B, T + 1, device=dev, dtype=torch.int64)
+            labels = torch.empty(B, T, device=dev, dtype=torch.int64) if bt.get("want_labels", True) else None
+            t.out_spans, t.out_labels, t.out_score, t.workspace = _ptr(spans), _ptr(labels), None, _ptr(ws)
+            keep.append(ws)
+            results.append((spans, labels, None))
+        elif mode == 1:
+            saved = torch.empty(lib.hsmm_logz_saved_bytes(B, T, C, K, flags), device=dev, dtype=torch.uint8)
+            logz = torch.empty(B, device=dev, dtype=torch.float64)
+            t.out_logz, t.saved = _ptr(logz), _ptr(saved)
+            results.append((logz, saved))
+        else:
+            if bt.get("out") is None:
+                d_init, d_trans, d_len = torch.zeros(C, device=dev), torch.zeros(C, C, device=dev), torch.zeros(K, C, device=dev)
+            else:
+                d_init, d_trans, d_len = bt["out"]
+            d_em = bt.get("d_em")
+            if d_em is None:
+                d_em = torch.empty(B, T, ldc, device=dev, dtype=torch.float32)
+            g = _f32(bt["grad"])
+            keep.append(g)
+            t.saved, t.grad_logz, t.d_init, t.d_trans, t.d_len, t.d_em = _ptr(bt["saved"]), _ptr(g), _ptr(d_init), _ptr(d_trans), \
+                _ptr(d_len), _ptr(d_em)
+            results.append((d_init, d_trans, d_len, d_em))
+    _lib.check(lib.hsmm_dp_grouped(mode, n, arr, _stream()), "hsmm_dp_grouped")
+    return results
 
 
 def weighted_feature_sums(features, weights, C, lengths_i32):

@@ -171,6 +171,8 @@ def make_task(C, cfg, gen, device, V=None, X=None, lengths=None):
     tk.lengths = lengths if lengths is not None else torch.randint(cfg["tmin"], cfg["tmax"] + 1, (V,), generator=gen)
     if lengths is None:
         tk.lengths[0] = cfg["tmax"]
+        if os.environ.get("HSMM_BENCH_BUCKETS"):
+            tk.lengths = torch.sort(tk.lengths, descending=True)[0]  # experiment: length buckets are contiguous slices
     Tmax = int(tk.lengths.max())
     tk.Tmax = Tmax
     tk.penalty = None
@@ -206,7 +208,11 @@ def make_task(C, cfg, gen, device, V=None, X=None, lengths=None):
 
 def make_workload(args, cfg, rank, device):
     gen = torch.Generator().manual_seed(args.seed + rank)
-    return [make_task(C, cfg, gen, device) for C in cfg["tasks"]]
+    classes = cfg["tasks"]
+    sel = os.environ.get("HSMM_BENCH_TASKS")  # experiment switch (echoed in config.env_switches): "small" = C <= 16, "large" = C > 16
+    if sel:
+        classes = [C for C in classes if (C <= 16) == (sel == "small")]
+    return [make_task(C, cfg, gen, device) for C in classes]
 
 
 def packed_layout(tasks):
@@ -220,7 +226,8 @@ def packed_layout(tasks):
 
 
 def env_switches():
-    return {k: os.environ[k] for k in ("HSMM_BENCH_SKIP", "HSMM_DISABLE_LIN", "HSMM_FORCE_GENERIC") if os.environ.get(k)}
+    return {k: os.environ[k] for k in ("HSMM_BENCH_SKIP", "HSMM_BENCH_TASKS", "HSMM_BENCH_BUCKETS", "HSMM_BENCH_GROUPS", "HSMM_DISABLE_LIN", "HSMM_DISABLE_PAIR", "HSMM_PAIR_MIN_VIDEOS",
+                                              "HSMM_FORCE_GENERIC") if os.environ.get(k)}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -275,11 +282,48 @@ def device_step(tasks, streams, packed, layout, world, reduce=True, decode_only=
             v.append(packed[o:o + m])
             o += m
         wx, d_trans, d_len, d_init, wsum, lz = v
+        nb = int(os.environ.get("HSMM_BENCH_BUCKETS", "0"))
+        xp = tk.penalty is not None
+        g = tk.gradw if world == 1 else tk.gradw / world
+        if nb > 1:
+            # experiment: the task's forward/backward in nb length-homogeneous sub-batches, each its own chain
+            ldc = em.shape[2]
+            with torch.cuda.stream(st):
+                d_em = torch.empty(tk.V, tk.Tmax, ldc, device=em.device)
+            lz_parts, evs = [], []
+            step_v = (tk.V + nb - 1) // nb
+            for j in range(nb):
+                a, b = j * step_v, min(tk.V, (j + 1) * step_v)
+                if a >= b:
+                    continue
+                sj = streams[(2 * n + i * nb + j) % ns] if j else st
+                if id(sj) not in forked:
+                    forked.add(id(sj))
+                    used.append(sj)
+                    sj.wait_event(fork)
+                sj.wait_event(em_ready)
+                with torch.cuda.stream(sj):
+                    sl = slice(a, b)
+                    lzj, savedj = hsmm.logz_forward(em[sl], tk.C, tk.init, tk.trans, tk.lenp, None if tk.end is None else tk.end[sl],
+                                                    offset[sl], tk.lengths_i32[sl], None, trans_pred=tk.pred, f64_state=xp)
+                    hsmm.logz_backward(em[sl], tk.C, tk.init, tk.trans, tk.lenp, None if tk.end is None else tk.end[sl],
+                                       tk.lengths_i32[sl], None, g[sl], savedj, out=(d_init, d_trans.view(tk.C, tk.C), d_len.view(tk.K, tk.C)),
+                                       trans_succ=tk.succ, f64_state=xp, d_em=d_em[sl])
+                    lz_parts.append(lzj.sum())
+                    ev = torch.cuda.Event()
+                    ev.record(sj)
+                    evs.append(ev)
+            with torch.cuda.stream(st):
+                for ev in evs:
+                    st.wait_event(ev)
+                hsmm._lib.check(lib.hsmm_weighted_feature_sums(hsmm._p(tk.X), hsmm._p(d_em), d_em.shape[2],
+                                                               hsmm._p(tk.lengths_i32), tk.V, tk.Tmax, tk.D, tk.C, hsmm._p(wx),
+                                                               hsmm._p(wsum), hsmm._stream()), "hsmm_weighted_feature_sums")
+                lz.copy_(torch.stack(lz_parts).sum().float().reshape(1))
+            continue
         with torch.cuda.stream(st):
-            xp = tk.penalty is not None
             logz, saved = hsmm.logz_forward(em, tk.C, tk.init, tk.trans, tk.lenp, tk.end, offset, tk.lengths_i32, tk.order,
                                             trans_pred=tk.pred, f64_state=xp)
-            g = tk.gradw if world == 1 else tk.gradw / world
             _, _, _, d_em = hsmm.logz_backward(em, tk.C, tk.init, tk.trans, tk.lenp, tk.end, tk.lengths_i32, tk.order, g,
                                                saved, out=(d_init, d_trans.view(tk.C, tk.C), d_len.view(tk.K, tk.C)),
                                                trans_succ=tk.succ, f64_state=xp)
@@ -293,6 +337,94 @@ def device_step(tasks, streams, packed, layout, world, reduce=True, decode_only=
         ev.record(st)
         cur.wait_event(ev)
     if world > 1 and reduce and not decode_only:
+        torch.distributed.all_reduce(packed)
+    return outs
+
+
+def grouped_eligible(tasks):
+    """hsmm_dp_grouped's envelope: sparse transition lists, K - 1 <= 20, C <= 32, one precision."""
+    return all(tk.chain and tk.K - 1 <= 20 and tk.C <= 32 for tk in tasks) and len({tk.penalty is not None for tk in tasks}) == 1
+
+
+def device_step_grouped(tasks, streams, packed, layout, world, reduce=True, n_groups=1):
+    """The same work as `device_step`, with the DP kernels of several tasks in ONE launch per kernel family
+    (hsmm_dp_grouped): per task emission scoring on the task's stream; per group of tasks {forward -> backward} on the
+    group's stream and Viterbi on a second one; per task the class-weighted feature sums once its group's backward
+    pass is done."""
+    from action_segmentation_b200 import hsmm
+    lib = hsmm._lib.load()
+    cur = torch.cuda.current_stream()
+    packed.zero_()
+    fork = torch.cuda.Event()
+    fork.record(cur)
+    n, ns = len(tasks), len(streams)
+    assert ns >= n + 2 * n_groups
+    em_out, em_ev = [], []
+    for i, tk in enumerate(tasks):
+        st = streams[i]
+        st.wait_event(fork)
+        with torch.cuda.stream(st):
+            em_out.append(hsmm.emission_scores(tk.X, tk.means, tk.cov_diag, tk.penalty, tk.lengths_i32, params=tk.eparams))
+            ev = torch.cuda.Event()
+            ev.record(st)
+            em_ev.append(ev)
+    xp = tasks[0].penalty is not None
+    outs = [None] * n
+    used = list(streams[:n])
+    for gi in range(n_groups):
+        idx = list(range(gi, n, n_groups))  # interleaved: every group gets small and large class sets
+        s_dp, s_vit = streams[n + gi], streams[n + n_groups + gi]
+        used += [s_dp, s_vit]
+        base = []
+        for i in idx:
+            tk = tasks[i]
+            em, rowterm, offset = em_out[i]
+            base.append(dict(em=em, C=tk.C, init=tk.init, trans=tk.trans, lenp=tk.lenp, end=tk.end, offset=offset,
+                             lengths_i32=tk.lengths_i32, order=tk.order, f64_state=xp))
+        for s_x in (s_dp, s_vit):
+            s_x.wait_event(fork)
+            for i in idx:
+                s_x.wait_event(em_ev[i])
+        with torch.cuda.stream(s_vit):
+            res = hsmm.grouped_dp(0, [dict(b, trans_list=tasks[i].pred, class_ids=tasks[i].class_ids) for b, i in zip(base, idx)])
+            for i, (spans, labels, _) in zip(idx, res):
+                outs[i] = (spans, labels, em_out[i][0], em_out[i][2])
+        with torch.cuda.stream(s_dp):
+            fw = hsmm.grouped_dp(1, [dict(b, trans_list=tasks[i].pred) for b, i in zip(base, idx)])
+            bw_in = []
+            for b, i, (logz, saved) in zip(base, idx, fw):
+                tk = tasks[i]
+                off, sizes = layout[i]
+                v, o = [], off
+                for m in sizes:
+                    v.append(packed[o:o + m])
+                    o += m
+                wx, d_trans, d_len, d_init, wsum, lz = v
+                g = tk.gradw if world == 1 else tk.gradw / world
+                bw_in.append(dict(b, trans_list=tk.succ, saved=saved, grad=g,
+                                  out=(d_init, d_trans.view(tk.C, tk.C), d_len.view(tk.K, tk.C))))
+            bw = hsmm.grouped_dp(2, bw_in)
+            bwd_done = torch.cuda.Event()
+            bwd_done.record(s_dp)
+        for i, (logz, saved), (_, _, _, d_em) in zip(idx, fw, bw):
+            tk = tasks[i]
+            off, sizes = layout[i]
+            wx = packed[off:off + sizes[0]]
+            o_ws = off + sum(sizes[:4])
+            wsum = packed[o_ws:o_ws + sizes[4]]
+            lz = packed[o_ws + sizes[4]:o_ws + sizes[4] + 1]
+            st = streams[i]
+            st.wait_event(bwd_done)
+            with torch.cuda.stream(st):
+                hsmm._lib.check(lib.hsmm_weighted_feature_sums(hsmm._p(tk.X), hsmm._p(d_em), d_em.shape[2],
+                                                               hsmm._p(tk.lengths_i32), tk.V, tk.Tmax, tk.D, tk.C, hsmm._p(wx),
+                                                               hsmm._p(wsum), hsmm._stream()), "hsmm_weighted_feature_sums")
+                lz.copy_(logz.sum().float().reshape(1))
+    for st in used:
+        ev = torch.cuda.Event()
+        ev.record(st)
+        cur.wait_event(ev)
+    if world > 1 and reduce:
         torch.distributed.all_reduce(packed)
     return outs
 
@@ -421,6 +553,39 @@ def kernel_breakdown(tasks, reps=3, decode_only=False):
                 for n in names:
                     launches[n] += 1
     return {n: sum(v for (k, _), v in best.items() if k == n) for n in names}, launches
+
+
+def kernel_breakdown_grouped(tasks, reps=3):
+    """As `kernel_breakdown` for the grouped step: emission and weighted sums per task, each DP pass as ONE grouped call."""
+    from action_segmentation_b200 import hsmm
+    best = {}
+
+    def timed(key, fn):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        r = fn()
+        b.record()
+        b.synchronize()
+        best[key] = min(best.get(key, 1e30), a.elapsed_time(b))
+        return r
+
+    xp = tasks[0].penalty is not None
+    for rep in range(reps):
+        ems = [timed(("emission", i), lambda: hsmm.emission_scores(tk.X, tk.means, tk.cov_diag, tk.penalty, tk.lengths_i32,
+                                                                  params=tk.eparams)) for i, tk in enumerate(tasks)]
+        base = [dict(em=e[0], C=tk.C, init=tk.init, trans=tk.trans, lenp=tk.lenp, end=tk.end, offset=e[2], lengths_i32=tk.lengths_i32,
+                     order=tk.order, f64_state=xp) for tk, e in zip(tasks, ems)]
+        fw = timed(("logz_forward", 0), lambda: hsmm.grouped_dp(1, [dict(b, trans_list=tk.pred) for b, tk in zip(base, tasks)]))
+        bw = timed(("logz_backward", 0), lambda: hsmm.grouped_dp(2, [dict(b, trans_list=tk.succ, saved=f[1], grad=tk.gradw)
+                                                                      for b, tk, f in zip(base, tasks, fw)]))
+        for i, (tk, r) in enumerate(zip(tasks, bw)):
+            timed(("weighted_feature_sums", i), lambda: hsmm.weighted_feature_sums(tk.X, r[3], tk.C, tk.lengths_i32))
+        timed(("viterbi", 0), lambda: hsmm.grouped_dp(0, [dict(b, trans_list=tk.pred, class_ids=tk.class_ids) for b, tk in zip(base, tasks)]))
+        del fw, bw
+    names = ["emission", "logz_forward", "logz_backward", "weighted_feature_sums", "viterbi"]
+    kms = {n: sum(v for (k, _), v in best.items() if k == n) for n in names}
+    launches = {n: sum(1 for (k, _) in best if k == n) for n in names}
+    return kms, launches
 
 
 def compute_ceiling(tasks, frames_per_s_per_gpu, sm_mhz, decode_only):
@@ -652,7 +817,15 @@ def run_train_decode(args, cfg, rank, world, device, barrier, sampler):
     frames = sum(tk.frames for tk in tasks)
     layout, total = packed_layout(tasks)
     packed = torch.zeros(total, device=device)
-    streams = [torch.cuda.Stream() for _ in range(min(2 * len(tasks), 36) + 1)]
+    n_groups = int(os.environ.get("HSMM_BENCH_GROUPS", "2"))
+    grouped = n_groups > 0 and grouped_eligible(tasks) and len(tasks) > 1 and not os.environ.get("HSMM_BENCH_SKIP")
+
+    def device_step(tasks, streams, packed, layout, world, reduce=True):  # noqa: F811 (the step of this run)
+        if grouped:
+            return device_step_grouped(tasks, streams, packed, layout, world, reduce=reduce, n_groups=n_groups)
+        return globals()["device_step"](tasks, streams, packed, layout, world, reduce=reduce)
+
+    streams = [torch.cuda.Stream() for _ in range(min(2 * len(tasks), 36) + 1 + 18 * int(os.environ.get("HSMM_BENCH_BUCKETS", "0")))]
     D = cfg["D"]
 
     # ---- device-resident throughput -------------------------------------------------------------
@@ -739,7 +912,7 @@ def run_train_decode(args, cfg, rank, world, device, barrier, sampler):
 
     # ---- per-kernel durations and the roofline of the dominant kernel ---------------------------
     peak_gbs, peak_src = peak_hbm()
-    kms, klaunch = kernel_breakdown(tasks)
+    kms, klaunch = kernel_breakdown_grouped(tasks) if grouped else kernel_breakdown(tasks)
     dom = max(kms, key=kms.get)
     meanC = sum(tk.C * tk.frames for tk in tasks) / float(frames)
     pen_bytes = 4.0 * meanC if cfg["narration"] else 0.0
@@ -756,7 +929,8 @@ def run_train_decode(args, cfg, rank, world, device, barrier, sampler):
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_frame": bpf,
                 "kernel_ms": {k: round(v, 3) for k, v in kms.items()}, "launches_per_step": klaunch,
-                "kernel_ms_note": "launches timed alone and serialised; in the step they overlap across streams",
+                "kernel_ms_note": "calls timed alone and serialised (API calls: a grouped DP call = its two or three kernels over all "
+                                  "tasks); in the step they overlap across streams",
                 # whole step against the same peak, per GPU (step_bytes counts this rank's frames)
                 "step_achieved_gbs": step_bytes / (ms_per_step * 1e-3) / 1e9, "step_frac": step_frac,
                 "compute_ceiling": comp, "binding": "fp32_issue" if comp["frac"] > step_frac else "hbm"}
@@ -778,6 +952,8 @@ def run_train_decode(args, cfg, rank, world, device, barrier, sampler):
                    sum(tk.V for tk in tasks), "parallelism": "dp%d over videos, 1 packed all-reduce/step%s" % (
                        world, " on a side stream, overlapping the next step (double-buffered statistics)" if world > 1 and graph is not None else ""),
                    "launch": "eager (Python)" if graph is None else "CUDA-graph replay of the step (captured after eager warm-up)",
+                   "dp_launches": ("hsmm_dp_grouped: one launch per kernel family over the %d tasks (%d group%s)" % (
+                       len(tasks), n_groups, "" if n_groups == 1 else "s")) if grouped else "one launch per task and kernel family",
                    "l2_policy": "inputs larger than L2 (%.1f GB of features per step per GPU)" % (frames * D * 4 / 1e9),
                    "dp_variants": sorted(set("%s | %s | %s" % tuple(_lib.dp_variant(tk.C, tk.K, m, tk.chain, tk.penalty is not None)
                                                                     for m in (0, 1, 2)) for tk in tasks))},
@@ -925,8 +1101,8 @@ def main():
         sw = env_switches()
         if sw:
             result["config"]["env_switches"] = sw
-            if "HSMM_BENCH_SKIP" in sw:
-                result["invalid"] = "ablation run: HSMM_BENCH_SKIP drops kernels from the timed region"
+            if "HSMM_BENCH_SKIP" in sw or "HSMM_BENCH_TASKS" in sw:
+                result["invalid"] = "ablation run: HSMM_BENCH_SKIP / HSMM_BENCH_TASKS drop work from the timed region"
         print(json.dumps(result))
     if world > 1:
         torch.distributed.destroy_process_group()

@@ -143,6 +143,29 @@ int hsmm_logz_backward(const float* em, int ldc, const float* init, const float*
                        float* d_init, float* d_trans, float* d_len, float* d_em, void* stream);
 
 /*
+ * Grouped DP launches: the Viterbi / forward / backward pass of SEVERAL task-homogeneous batches in one call.
+ * The reference trains on mini-batches of one task at a time (data/corpus.py:613-644; models/semimarkov/semimarkov.py:
+ * 222-266): every batch has its own class set, hence its own init / trans / len tables.  Calling the three entry points
+ * above once per batch launches kernels that each keep only a few dozen CTAs busy for as long as that batch's longest
+ * video lasts.  Here one kernel per family covers all the batches (parameter blocks indexed by block id), which is what
+ * fills a B200 when a whole split is decoded or a large step is taken.
+ *   mode 0: hsmm_viterbi, 1: hsmm_logz_forward, 2: hsmm_logz_backward -- same semantics, same buffers per task.
+ * Envelope: every task needs its sparse transition list (`trans_list` = predecessors for modes 0 and 1, successors for
+ * mode 2), K - 1 <= 20, C <= 32, ldc = C rounded up to 4, and the same `flags` for all tasks; n <= 32 tasks per call.
+ * Outside the envelope the call returns HSMM_ERR_SHAPE and the caller uses the per-batch entry points.
+ */
+typedef struct {
+    const float* em; int ldc;
+    const float* init; const float* trans; const int32_t* trans_list; const float* lenp; const float* end;
+    const double* offset; const int32_t* lengths; const int32_t* order; const int32_t* class_ids;
+    int B, Tmax, C, K, flags;
+    int64_t* out_spans; int64_t* out_labels; double* out_score; void* workspace;   /* mode 0 */
+    double* out_logz; void* saved;                                                   /* modes 1, 2 */
+    const float* grad_logz; float* d_init; float* d_trans; float* d_len; float* d_em; /* mode 2 */
+} hsmm_dp_task;
+int hsmm_dp_grouped(int mode, int n, const hsmm_dp_task* tasks, void* stream);
+
+/*
  * Class-weighted feature sums.  The reduction behind d loss / d gaussian_means (autograd through
  * emission_log_probs, semimarkov_modules.py:324-381) and behind the supervised class means
  * r^T X of semimarkov_sufficient_stats (semimarkov_utils.py:74-126):
@@ -214,6 +237,13 @@ int hsmm_set_generic_dp(int force);
  * returns the previous setting.  Environment: HSMM_DISABLE_LIN=1.  hsmm_dp_variant reports "lin+" in front
  * of the variant name when the linear-window kernel is used for that shape. */
 int hsmm_set_linear_window(int enabled);
+
+/* Chain-constrained shapes with C <= 16 classes and K - 1 <= 20 have a second fast path that carries TWO videos per warp
+ * (1.6-1.7x fewer instructions per frame); it is used when a call (or a whole hsmm_dp_grouped group) has at least this
+ * many videos -- below that a launch is latency-bound and the one-video-per-warp kernels finish sooner.  Default 4096
+ * (environment: HSMM_PAIR_MIN_VIDEOS); 0 = always, negative = never.  Results do not depend on it.  Returns the
+ * previous value. */
+int hsmm_set_pair_min_videos(int n);
 
 #ifdef __cplusplus
 }

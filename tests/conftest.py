@@ -21,3 +21,12 @@ def golden():
         return dict(np.load(os.path.join(GOLDEN, name + ".npz")))
 
     return load
+
+
+@pytest.fixture(params=["one_video_per_warp", "two_videos_per_warp"])
+def pair_mode(request):
+    """Run a test on both fast paths of the C <= 16 chain-constrained shapes (hsmm_set_pair_min_videos)."""
+    import action_segmentation_b200 as pkg
+    prev = pkg._lib.set_pair_min_videos(0 if request.param == "two_videos_per_warp" else -1)
+    yield request.param
+    pkg._lib.set_pair_min_videos(prev)

@@ -211,3 +211,62 @@ def test_full_size_narration_f64_state_vs_oracle():
     sp = sparse_lists(prob)
     logz, counts, w = run_logz_and_counts(prob, sp=sp, f64_state=True)
     check_against_oracle(prob, logz, counts, w, tol=5e-4)  # see test_full_size_vs_oracle
+
+
+# ---------------------------------------------------------------------------------------------
+# grouped launches (hsmm_dp_grouped): several task-homogeneous batches in one kernel per family
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("f64_state", [False, True], ids=["f32state", "f64state"])
+def test_grouped_launch_equals_per_batch_calls_and_oracle(f64_state, pair_mode):
+    """Five batches with different class sets (C = 7, 13, 16, 17, 23: both the two-videos-per-warp and the one-warp
+    kernels), chain constraints with per-video end states, one of them with videos too short for its chain (those are
+    flagged and re-run by the grouped log-domain kernel): Viterbi spans identical to the per-batch entry point,
+    logZ and the four count tensors equal to the per-batch calls (atomics: summation order) and to the fp64 oracle."""
+    H = pkg.hsmm
+    rng = np.random.default_rng(17)
+    probs, devs, sps = [], [], []
+    for (B, Tmax, C) in [(9, 70, 7), (6, 90, 13), (5, 60, 16), (7, 80, 17), (8, 100, 23)]:
+        prob = random_problem(rng, B, Tmax, C, 20, Tmin=25, chain=True, ends=True, narration=f64_state)
+        if C == 13:
+            prob["lengths"][2] = 4  # shorter than the chain: an extra end state exists for it (helpers.random_problem)
+            prob["end"][2, :] = O.BIG_NEG
+            prob["end"][2, 3] = 0.0
+        prob["lenp"] = O.clamp_len_table(prob["lenp"], Tmax)
+        probs.append(prob)
+        devs.append(to_dev(prob))
+        sps.append(sparse_lists(prob))
+    base = [dict(em=d["em"], C=d["C"], init=d["init"], trans=d["trans"], lenp=d["lenp"], end=d["end"], offset=None,
+                 lengths_i32=d["lengths_i32"], order=d["order"], f64_state=f64_state) for d in devs]
+    # Viterbi
+    res = H.grouped_dp(0, [dict(b, trans_list=sp[0]) for b, sp in zip(base, sps)])
+    for (spans, labels, _), d, sp, prob in zip(res, devs, sps, probs):
+        ref_spans, ref_labels, _ = H.viterbi_decode(d["em"], d["C"], d["init"], d["trans"], d["lenp"], d["end"], None,
+                                                    d["lengths_i32"], d["order"], trans_pred=sp[0], want_score=False)
+        assert torch.equal(spans, ref_spans) and torch.equal(labels, ref_labels)
+        check_viterbi_against_oracle(prob, spans.cpu().numpy())
+    # forward + backward
+    fw = H.grouped_dp(1, [dict(b, trans_list=sp[0]) for b, sp in zip(base, sps)])
+    ws = [torch.from_numpy(rng.uniform(0.5, 1.5, size=d["em"].shape[0])).float().cuda() for d in devs]
+    bw = H.grouped_dp(2, [dict(b, trans_list=sp[1], saved=saved, grad=w) for b, sp, (logz, saved), w in zip(base, sps, fw, ws)])
+    for (logz, saved), (d_init, d_trans, d_len, d_em), d, sp, prob, w in zip(fw, bw, devs, sps, probs, ws):
+        C = d["C"]
+        lz1, saved1 = H.logz_forward(d["em"], C, d["init"], d["trans"], d["lenp"], d["end"], None, d["lengths_i32"], d["order"],
+                                     trans_pred=sp[0], f64_state=f64_state)
+        one = H.logz_backward(d["em"], C, d["init"], d["trans"], d["lenp"], d["end"], d["lengths_i32"], d["order"], w, saved1,
+                              trans_succ=sp[1], f64_state=f64_state)
+        # flagged videos are re-run by the log-domain kernel of the GROUP's variant (<20,1>), per batch by the batch's own
+        assert torch.allclose(logz, lz1, rtol=1e-7, atol=1e-5)
+        for a, b_ in zip((d_init, d_trans, d_len, d_em), one):
+            assert torch.allclose(a, b_, rtol=1e-5, atol=1e-5)  # C <= 16: the group runs <KR=20,S=1>, the batch <KR=10,S=2>
+        check_against_oracle(prob, logz.cpu().numpy(), dict(E_init=d_init, E_trans=d_trans, E_len=d_len, E_em=d_em[:, :, :C]),
+                             w.cpu().numpy().astype(np.float64))
+
+
+def test_grouped_launch_rejects_shapes_outside_its_envelope():
+    H = pkg.hsmm
+    rng = np.random.default_rng(3)
+    prob = random_problem(rng, 3, 60, 9, 40, Tmin=50, chain=True, ends=True)   # K - 1 = 39 > 20
+    d, sp = to_dev(prob), sparse_lists(prob)
+    with pytest.raises(pkg.HsmmError):
+        H.grouped_dp(1, [dict(em=d["em"], C=9, init=d["init"], trans=d["trans"], lenp=d["lenp"], end=d["end"], offset=None,
+                              lengths_i32=d["lengths_i32"], order=d["order"], trans_list=sp[0])])

@@ -87,7 +87,7 @@ def test_emission_tensor_core_vs_oracle(B, Tmax, D, C, pen):
 
 
 @pytest.mark.parametrize("case", CASES)
-def test_loglik_and_grads_golden(golden, case):
+def test_loglik_and_grads_golden(golden, case, pair_mode):
     """logZ, its batch mean and the four parameter gradients: within 1e-4 relative of the reference's
     fp32 values, and tighter against the fp64 oracle."""
     g = golden(case)
@@ -111,7 +111,7 @@ def test_loglik_and_grads_golden(golden, case):
 
 
 @pytest.mark.parametrize("case", CASES + ["supervised_decode"])
-def test_viterbi_golden(golden, case):
+def test_viterbi_golden(golden, case, pair_mode):
     g = golden(case)
     m = module_from_golden(g)
     feats, lengths, vpi, addl, cons = _inputs(g)
@@ -178,7 +178,7 @@ SHAPES = [
 
 
 @pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "B%d_T%d_C%d_K%d" % s[:4])
-def test_viterbi_random_vs_oracle(shape):
+def test_viterbi_random_vs_oracle(shape, pair_mode):
     import action_segmentation_b200 as pkg
     B, Tmax, C, K, chain, ends = shape
     rng = np.random.default_rng(100 + C * 7 + K)
@@ -199,7 +199,7 @@ def test_viterbi_random_vs_oracle(shape):
 
 @pytest.mark.parametrize("f64_state", [False, True], ids=["f32state", "f64state"])
 @pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "B%d_T%d_C%d_K%d" % s[:4])
-def test_logz_and_counts_random_vs_oracle(shape, f64_state):
+def test_logz_and_counts_random_vs_oracle(shape, f64_state, pair_mode):
     """logZ within 1e-5 relative, expected counts within 1e-4 relative of the fp64 oracle.  With the f64-state
     kernels (HSMM_FLAG_F64_STATE, what the module selects whenever narration constraints are given) the
     ordering-constrained shapes also carry -1e4 narration penalties on (nearly) every path -- inputs on which
@@ -229,7 +229,7 @@ def test_logz_and_counts_random_vs_oracle(shape, f64_state):
 
 
 @pytest.mark.parametrize("C,K", [(9, 20), (23, 20), (23, 100)])
-def test_sparse_hint_degenerate_falls_back_to_dense(C, K):
+def test_sparse_hint_degenerate_falls_back_to_dense(C, K, pair_mode):
     """Videos with NO path through the unmasked transitions (chain longer than the video, no extra
     allowed end): the sparse kernels must notice (result <= -1e8) and reproduce the dense answer, which
     itself must agree with the oracle on the -1e9-penalised problem."""
@@ -456,7 +456,7 @@ LIN_SHAPES = [
 
 
 @pytest.mark.parametrize("shape", LIN_SHAPES, ids=lambda s: "B%d_T%d_C%d_K%d_s%g" % (s[0], s[1], s[2], s[3], s[6]))
-def test_linear_window_matches_log_domain_and_oracle(shape):
+def test_linear_window_matches_log_domain_and_oracle(shape, pair_mode):
     """Same inputs through the linear-window kernels and (hsmm_set_linear_window(0)) the log-domain kernels: logZ,
     every expected count and the frame posteriors agree to fp32 rounding, and both agree with the fp64 oracle."""
     import action_segmentation_b200 as pkg
@@ -497,7 +497,7 @@ def test_linear_window_matches_log_domain_and_oracle(shape):
 
 
 @pytest.mark.parametrize("case", ["tiny_rates", "no_self_loops", "no_path", "collapse"])
-def test_linear_window_flags_fall_back_to_log_domain(case):
+def test_linear_window_flags_fall_back_to_log_domain(case, pair_mode):
     """Inputs the float window cannot certify: the videos are flagged, recomputed by the log-domain kernels, and the
     results still match the oracle."""
     import action_segmentation_b200 as pkg
@@ -565,7 +565,7 @@ VIT2_SHAPES = [
 
 
 @pytest.mark.parametrize("shape", VIT2_SHAPES, ids=lambda s: "B%d_T%d_C%d_K%d_s%g" % (s[0], s[1], s[2], s[3], s[6]))
-def test_viterbi_deferred_argmax_identical_to_generic_kernel(shape):
+def test_viterbi_deferred_argmax_identical_to_generic_kernel(shape, pair_mode):
     """The deferred-arg-max kernel rebuilds the sweep's candidates bit for bit during the back-trace: spans, labels
     and scores must be IDENTICAL to dp_forward_kernel<VIT> (hsmm_set_linear_window(0)), and match the oracle."""
     import action_segmentation_b200 as pkg
