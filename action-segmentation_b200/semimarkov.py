@@ -369,22 +369,29 @@ class SemiMarkovModel(object):
     # -- decoding -------------------------------------------------------------------------------
     def predict(self, test_data):
         """models/semimarkov/semimarkov.py:318-410.  Per-frame labels (global class ids) come straight from the
-        Viterbi kernel; every batch's kernels and result copies are enqueued back to back and the host
-        synchronises once for the whole split."""
+        Viterbi kernel; up to 32 mini-batches are decoded by one grouped launch (SemiMarkovModule.viterbi_batches), the
+        result copies are enqueued back to back and the host synchronises once for the whole split."""
         self.model.eval()
         predictions = {}
         loader = self._loader(test_data, shuffle=False, batch_by_task=True, batch_size=self.args.batch_size)
-        queued = []
+        queued, pending = [], []
+
+        def flush():
+            res = self.model.viterbi_batches([p[0] for p in pending], return_labels=True, return_spans=False, non_blocking=True)
+            for (_, labels), (_, videos, lengths) in zip(res, pending):
+                queued.append((videos, labels, lengths))
+            pending.clear()
+
         for batch in self._device_batches(test_data, loader):
             tasks, lengths = batch['task_name'], batch['lengths']
             assert len(set(tasks)) == 1
-            constraints = self._narration(test_data, batch, 'test')
-            addl = self.make_additional_allowed_ends(tasks, lengths)
-            _, labels = self.model.viterbi(batch['features'], lengths, batch['task_indices'],
-                                           add_eos=True, use_mean_z=True, additional_allowed_ends_per_instance=addl,
-                                           constraints=constraints, return_labels=True, non_blocking=True,
-                                           return_spans=False)
-            queued.append((batch['video_name'], labels, lengths))
+            pending.append((dict(features=batch['features'], lengths=lengths, valid_classes_per_instance=batch['task_indices'],
+                                 additional_allowed_ends_per_instance=self.make_additional_allowed_ends(tasks, lengths),
+                                 constraints=self._narration(test_data, batch, 'test')), batch['video_name'], lengths))
+            if len(pending) >= self.model.GROUP_MAX:
+                flush()
+        if pending:
+            flush()
         torch.cuda.current_stream().synchronize()  # all label copies have landed in pinned memory
         for videos, labels, lengths in queued:
             labels = labels.numpy()

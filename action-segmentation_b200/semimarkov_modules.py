@@ -537,6 +537,44 @@ class SemiMarkovModule(nn.Module):
             out.append(self._to_host(labels, non_blocking))
         return out[0] if len(out) == 1 else tuple(out)
 
+    GROUP_MAX = 32  # hsmm_dp_grouped: batches per call
+
+    def viterbi_batches(self, batches, return_labels=True, return_spans=True, non_blocking=True):
+        """`viterbi` for a LIST of batches (dicts with features, lengths, valid_classes_per_instance and optionally
+        additional_allowed_ends_per_instance, constraints): emission scoring per batch, then ONE grouped Viterbi launch
+        per kernel family for up to 32 batches at a time (hsmm_dp_grouped) when the batches are inside its envelope --
+        ordering-constrained transitions, max span <= 21, <= 32 valid classes, which is the reference's U7 setting --
+        and per-batch launches otherwise.  This is the decode of a whole split (models/semimarkov/semimarkov.py:318-410
+        loops over mini-batches of 5 videos).  Returns a list of (spans, labels) like `viterbi(return_labels=True)`."""
+        prepared = []
+        with torch.no_grad():
+            for bt in batches:
+                valid_classes, C = self._valid_classes(bt['valid_classes_per_instance'])
+                scores, _ = self.score_features(bt['features'], bt['lengths'], valid_classes, add_eos=True, use_mean_z=True,
+                                                additional_allowed_ends_per_instance=bt.get('additional_allowed_ends_per_instance'),
+                                                constraints=bt.get('constraints'))
+                prepared.append((scores, C))
+            results = [None] * len(prepared)
+            todo = [i for i, (sc, C) in enumerate(prepared)
+                    if sc.sparse is not None and sc.lenp.shape[0] - 1 <= 20 and C <= 32]
+            for a in range(0, len(todo), self.GROUP_MAX):
+                chunk = todo[a:a + self.GROUP_MAX]
+                res = hsmm.grouped_dp(0, [dict(em=prepared[i][0].em, C=prepared[i][1], init=prepared[i][0].init,
+                                               trans=prepared[i][0].trans, lenp=prepared[i][0].lenp, end=prepared[i][0].end,
+                                               offset=prepared[i][0].offset, lengths_i32=prepared[i][0].lengths_i32,
+                                               order=prepared[i][0].order, trans_list=prepared[i][0].sparse[0],
+                                               class_ids=prepared[i][0].decode_ids, want_labels=return_labels) for i in chunk])
+                for i, (spans, labels, _) in zip(chunk, res):
+                    results[i] = (spans, labels)
+            for i, (sc, C) in enumerate(prepared):
+                if results[i] is None:
+                    spans, labels, _ = hsmm.viterbi_decode(sc.em, C, sc.init, sc.trans, sc.lenp, sc.end, sc.offset, sc.lengths_i32,
+                                                           sc.order, sc.decode_ids, want_labels=return_labels, want_score=False,
+                                                           trans_pred=None if sc.sparse is None else sc.sparse[0])
+                    results[i] = (spans, labels)
+        return [(self._to_host(sp, non_blocking) if return_spans else None,
+                 self._to_host(lab, non_blocking) if return_labels else None) for sp, lab in results]
+
     def log_likelihood_and_viterbi(self, features, lengths, valid_classes_per_instance, add_eos=True,
                                    additional_allowed_ends_per_instance=None, constraints=None, non_blocking=False):
         """`log_likelihood(spans=None)` and `viterbi(return_labels=True)` of the same batch with ONE emission pass

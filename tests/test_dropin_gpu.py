@@ -356,3 +356,34 @@ def test_combined_loglik_and_viterbi_equals_separate_calls():
     for k, p in m.named_parameters():
         if p.grad is not None:
             assert torch.allclose(p.grad, grads[k], rtol=1e-4, atol=1e-5), k  # atomics: summation order varies
+
+
+def test_viterbi_batches_grouped_equals_per_batch_viterbi():
+    """SemiMarkovModule.viterbi_batches (one grouped launch for up to 32 mini-batches of different tasks) against
+    `viterbi` called batch by batch; a second model without transition constraints takes the per-batch route."""
+    split = data.make_crosstask_like(n_tasks=4, steps_per_task=(2, 6), n_videos=37, feature_dim=10, frames=(30, 90), narration=True,
+                                     seed=21, allow_short=True)
+    for constrained in (True, False):
+        args = HsmmArgs(sm_max_span_length=15, sm_constrain_transitions=constrained, annotate_background_with_previous=True,
+                        sm_constrain_with_narration=['test'], batch_size=3)
+        torch.manual_seed(7)
+        model = pkg.SemiMarkovModel.from_args(args, split)
+        with torch.no_grad():
+            model.model.gaussian_means.normal_()
+            model.model.transition_logits.normal_()
+            model.model.poisson_log_rates.uniform_(0.5, 2.0)
+        loader = model._loader(split, shuffle=False, batch_by_task=True, batch_size=3)
+        batches = []
+        for batch in model._device_batches(split, loader):
+            batches.append(dict(features=batch['features'], lengths=batch['lengths'], valid_classes_per_instance=batch['task_indices'],
+                                additional_allowed_ends_per_instance=model.make_additional_allowed_ends(batch['task_name'], batch['lengths']),
+                                constraints=model._narration(split, batch, 'test')))
+        assert len(batches) > 8
+        grouped = model.model.viterbi_batches(batches, non_blocking=False)
+        for bt, (spans, labels) in zip(batches, grouped):
+            ref_spans, ref_labels = model.model.viterbi(bt['features'], bt['lengths'], bt['valid_classes_per_instance'],
+                                                        additional_allowed_ends_per_instance=bt['additional_allowed_ends_per_instance'],
+                                                        constraints=bt['constraints'], return_labels=True)
+            assert torch.equal(spans, ref_spans) and torch.equal(labels, ref_labels)
+        pred = model.predict(split)
+        assert len(pred) == 37 and all(len(pred[v['video_name']]) == v['features'].shape[0] for v in split.videos)
