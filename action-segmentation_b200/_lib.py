@@ -24,7 +24,7 @@ class DpTask(ctypes.Structure):
                 ("B", _i), ("Tmax", _i), ("C", _i), ("K", _i), ("flags", _i),
                 ("out_spans", _p), ("out_labels", _p), ("out_score", _p), ("workspace", _p),
                 ("out_logz", _p), ("saved", _p),
-                ("grad_logz", _p), ("d_init", _p), ("d_trans", _p), ("d_len", _p), ("d_em", _p)]
+                ("grad_logz", _p), ("d_init", _p), ("d_trans", _p), ("d_len", _p), ("d_em", _p), ("trans_list2", _p)]
 
 
 class HsmmError(RuntimeError):

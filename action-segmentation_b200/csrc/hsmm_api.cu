@@ -302,7 +302,7 @@ int hsmm_logz_backward(const float* em, int ldc, const float* init, const float*
 }
 
 int hsmm_dp_grouped(int mode, int n, const hsmm_dp_task* tasks, void* stream) {
-    if (!tasks || n <= 0 || mode < 0 || mode > 2) {
+    if (!tasks || n <= 0 || mode < 0 || mode > 3) {
         set_error("hsmm_dp_grouped: bad arguments (mode=%d n=%d)", mode, n);
         return HSMM_ERR_ARG;
     }
@@ -339,18 +339,19 @@ int hsmm_dp_grouped(int mode, int n, const hsmm_dp_task* tasks, void* stream) {
             p.vflag = p.vdelta + (size_t)t.B * (t.Tmax + 1);
             p.score = t.out_score; p.trans_pred = t.trans_list;
         } else {
-            if (!t.saved || (mode == 1 && !t.out_logz) ||
-                (mode == 2 && (!t.grad_logz || !t.d_init || !t.d_trans || !t.d_len || !t.d_em))) {
+            if (!t.saved || ((mode == 1 || mode == 3) && !t.out_logz) ||
+                (mode >= 2 && (!t.grad_logz || !t.d_init || !t.d_trans || !t.d_len || !t.d_em)) || (mode == 3 && !t.trans_list2)) {
                 set_error("hsmm_dp_grouped: task %d: missing buffer for mode %d", i, mode);
                 return HSMM_ERR_ARG;
             }
             p.xp = (t.flags & HSMM_FLAG_F64_STATE) ? 1 : 0;
             Saved sv = carve(t.saved, t.B, t.Tmax, t.C, p.xp != 0);
             p.fbeta = sv.fbeta; p.fgamma = sv.fgamma; p.fdelta = sv.fdelta; p.logz2 = sv.logz2; p.fflag = sv.fflag; p.bflag = sv.bflag;
-            if (mode == 1) {
+            if (mode == 1 || mode == 3) {
                 p.logz = t.out_logz; p.trans_pred = t.trans_list;
-            } else {
-                p.trans_succ = t.trans_list; p.grad = t.grad_logz;
+            }
+            if (mode >= 2) {
+                p.trans_succ = mode == 3 ? t.trans_list2 : t.trans_list; p.grad = t.grad_logz;
                 p.d_init = t.d_init; p.d_trans = t.d_trans; p.d_len = t.d_len; p.d_em = t.d_em;
             }
         }

@@ -16,6 +16,27 @@ namespace hsmm {
 bool dp_lin_enabled();
 bool dp_pair_enabled_for(int videos);
 
+// Forward and backward pass of a video back to back in ONE launch: a video's backward pass starts when ITS forward pass
+// ends instead of when the longest video of the launch has finished its forward pass, so the SMs stay full while the
+// long videos are still going forward (the saved planes it reads back were written by the same warp: L2-coherent loads).
+// A video the forward pass flags (fflag) is skipped by the backward body and left, with its backward pass, to the
+// log-domain kernels launched behind.
+template <bool XP>
+__global__ void __launch_bounds__(128, XP ? 1 : 4) dp_lin_fb_kernel_grouped(const __grid_constant__ DpGroup g) {
+    int local;
+    const int t = group_find(g, blockIdx.x, local);
+    dp_lin_forward_kernel_body<XP, 20, 1, 2>(g.t[t], local);
+    __syncwarp();
+    dp_lin_backward_kernel_body<XP, 20, 1, 2>(g.t[t], local);
+}
+__global__ void __launch_bounds__(128, 4) dp_pair_fb_kernel_grouped(const __grid_constant__ DpGroup g) {
+    int local;
+    const int t = group_find(g, blockIdx.x, local);
+    dp_pair_forward_kernel_body<PAIR_KR>(g.t[t], local);
+    __syncwarp();
+    dp_pair_backward_kernel_body<PAIR_KR>(g.t[t], local);
+}
+
 static int fill_group(DpGroup& g, const DpParams* ps, const int* idx, int n, int videos_per_block, int only_flagged) {
     g.n = n;
     int first = 0;
@@ -46,7 +67,9 @@ static int launch_generic(DpGroup& g, int blocks, int mode, size_t smem, cudaStr
 template <bool XP>
 static int launch_lin_group(DpGroup& g, int blocks, int mode, cudaStream_t st) {
     const size_t smem = 4 * (2 * 32 + 2) * sizeof(float);
-    if (mode == 0)
+    if (mode == 3)
+        dp_lin_fb_kernel_grouped<XP><<<blocks, 128, smem, st>>>(g);
+    else if (mode == 0)
         dp_vit2_kernel_grouped<20, 1, 2><<<blocks, 128, smem, st>>>(g);
     else if (mode == 1)
         dp_lin_forward_kernel_grouped<XP, 20, 1, 2><<<blocks, 128, smem, st>>>(g);
@@ -56,7 +79,9 @@ static int launch_lin_group(DpGroup& g, int blocks, int mode, cudaStream_t st) {
 }
 
 static int launch_pair_group(DpGroup& g, int blocks, int mode, cudaStream_t st) {
-    if (mode == 0)
+    if (mode == 3)
+        dp_pair_fb_kernel_grouped<<<blocks, 128, 0, st>>>(g);
+    else if (mode == 0)
         dp_pair_vit_kernel_grouped<PAIR_KR><<<blocks, 128, 0, st>>>(g);
     else if (mode == 1)
         dp_pair_forward_kernel_grouped<PAIR_KR><<<blocks, 128, 0, st>>>(g);
@@ -76,12 +101,13 @@ int dp_group_launch(const DpParams* ps, int n, int mode, cudaStream_t st) {
     for (int i = 0; i < n; ++i) {
         const DpParams& p = ps[i];
         const int32_t* list = mode == 2 ? p.trans_succ : p.trans_pred;
+        if (mode == 3 && !p.trans_succ) list = nullptr;
         if (!list || p.L > 20 || p.C > 32 || (mode != 0 && (p.xp != 0) != xp)) {
             set_error("grouped DP launch: task %d is outside the envelope (sparse transition lists, K-1 <= 20, C <= 32, one precision): "
                       "C=%d K=%d list=%p", i, p.C, p.L + 1, (const void*)list);
             return -2;
         }
-        const size_t sm = smem_bytes(kVariants[1], p.C, 1, 4, 2, mode, xp);
+        const size_t sm = smem_bytes(kVariants[1], p.C, 1, 4, 2, mode == 3 ? 2 : mode, xp);
         if (sm > smem) smem = sm;
     }
     static thread_local DpGroup g;  // 9.6 KB: kept off the stack; the launch copies it
@@ -114,6 +140,11 @@ int dp_group_launch(const DpParams* ps, int n, int mode, cudaStream_t st) {
     // the log-domain kernels: the whole job when the linear-window kernels are switched off, otherwise only the videos
     // those kernels flagged (their warps exit at once for every other video)
     const int blocks = fill_group(g, ps, all, n, 4, lin ? 1 : 0);
+    if (mode == 3) {
+        rc = xp ? launch_generic<true>(g, blocks, 1, smem, st) : launch_generic<false>(g, blocks, 1, smem, st);
+        if (rc) return rc;
+        return xp ? launch_generic<true>(g, blocks, 2, smem, st) : launch_generic<false>(g, blocks, 2, smem, st);
+    }
     return xp ? launch_generic<true>(g, blocks, mode, smem, st) : launch_generic<false>(g, blocks, mode, smem, st);
 }
 

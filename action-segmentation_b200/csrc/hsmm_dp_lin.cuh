@@ -313,7 +313,7 @@ __device__ __forceinline__ void dp_lin_backward_kernel_body(const DpParams& p, c
     if (vidx >= p.B) return;
     const int b = p.order ? p.order[vidx] : vidx;
     const int T = p.lengths[b];
-    if (((int)p.fflag[b]) & 1) {  // the forward pass fell back to the dense matrix: so does the backward pass
+    if (((int)p.fflag[b]) & 3) {  // the forward pass fell back to the dense matrix: so does the backward pass
         if (lane == 0) p.bflag[b] = 1.0f;
         return;
     }
@@ -381,7 +381,7 @@ __device__ __forceinline__ void dp_lin_backward_kernel_body(const DpParams& p, c
     ST zprev = NEG;                               // zeta^[n+1][c]
     ST rref = 0, eprev = 0;
     float occ = 0.0f, comp = 0.0f;
-    float Fprev = valid ? w * ex2((float)(__ldg(fg0 + (size_t)T * ldc) + (ST)endc - lzrel)) : 0.0f;
+    float Fprev = valid ? w * ex2((float)(__ldcg(fg0 + (size_t)T * ldc) + (ST)endc - lzrel)) : 0.0f;
     float Sprev = 0.0f;
     float gm_next = 0.0f;
     float S0 = 0.0f;
@@ -404,9 +404,9 @@ __device__ __forceinline__ void dp_lin_backward_kernel_body(const DpParams& p, c
         const int nn = T - 1 - f;
         const bool ok = valid && nn > 0;
         enext[f] = (valid && nn >= 0) ? __ldg(pe - f * ldc) : 0.0f;
-        bnext[f] = ok ? __ldg(pb - f * ldc) : (ST)0;
-        gnext[f] = ok ? __ldg(pg - f * ldc) : (ST)0;
-        dnext[f] = (nn >= 1) ? __ldg(pd - f) : 0.0f;
+        bnext[f] = ok ? __ldcg(pb - f * ldc) : (ST)0;
+        gnext[f] = ok ? __ldcg(pg - f * ldc) : (ST)0;
+        dnext[f] = (nn >= 1) ? __ldcg(pd - f) : 0.0f;
     }
 
 #pragma unroll 1
@@ -429,9 +429,9 @@ __device__ __forceinline__ void dp_lin_backward_kernel_body(const DpParams& p, c
             const int nn = n0 - FB - f;
             const bool ok = valid && nn > 0;
             enext[f] = (valid && nn >= 0) ? __ldg(pe - f * ldc) : 0.0f;
-            bnext[f] = ok ? __ldg(pb - f * ldc) : (ST)0;
-            gnext[f] = ok ? __ldg(pg - f * ldc) : (ST)0;
-            dnext[f] = (nn >= 1) ? __ldg(pd - f) : 0.0f;
+            bnext[f] = ok ? __ldcg(pb - f * ldc) : (ST)0;
+            gnext[f] = ok ? __ldcg(pg - f * ldc) : (ST)0;
+            dnext[f] = (nn >= 1) ? __ldcg(pd - f) : 0.0f;
         }
 #pragma unroll
         for (int f = 0; f < FB; ++f) {

@@ -227,7 +227,7 @@ __device__ __forceinline__ void dp_pair_backward_kernel_body(const DpParams& p, 
     const int sub = q.sub, c = q.c, b = q.b, T = q.T;
     const float SC = LOG2E;
     // a video whose forward pass fell back to the dense matrix is left to the log-domain kernel (as in dp_lin_backward)
-    const bool dense_fwd = q.have && (((int)p.fflag[b]) & 1);
+    const bool dense_fwd = q.have && (((int)p.fflag[b]) & 3);
     if (dense_fwd && c == 0) p.bflag[b] = 1.0f;
     const bool have = q.have && !dense_fwd;
     const bool valid = have && c < C;
@@ -277,7 +277,7 @@ __device__ __forceinline__ void dp_pair_backward_kernel_body(const DpParams& p, 
     float eta = valid ? endc - lzrel : NEG;
     float zprev = NEG, rref = 0.0f, eprev = 0.0f;
     float occ = 0.0f, comp = 0.0f;
-    float Fprev = valid ? w * ex2(__ldg(fg0 + (size_t)T * ldc) + endc - lzrel) : 0.0f;
+    float Fprev = valid ? w * ex2(__ldcg(fg0 + (size_t)T * ldc) + endc - lzrel) : 0.0f;
     float Sprev = 0.0f, gm_next = 0.0f, S0 = 0.0f;
     LinTracker trk;
     trk.init();
@@ -298,9 +298,9 @@ __device__ __forceinline__ void dp_pair_backward_kernel_body(const DpParams& p, 
         const int nn = T - 1 - f;
         const bool ok = valid && nn > 0;
         enext[f] = (valid && nn >= 0) ? __ldg(pe - f * ldc) : 0.0f;
-        bnext[f] = ok ? __ldg(pb - f * ldc) : 0.0f;
-        gnext[f] = ok ? __ldg(pg - f * ldc) : 0.0f;
-        dnext[f] = (have && nn >= 1) ? __ldg(pd - f) : 0.0f;
+        bnext[f] = ok ? __ldcg(pb - f * ldc) : 0.0f;
+        gnext[f] = ok ? __ldcg(pg - f * ldc) : 0.0f;
+        dnext[f] = (have && nn >= 1) ? __ldcg(pd - f) : 0.0f;
     }
 
 #pragma unroll 1
@@ -322,9 +322,9 @@ __device__ __forceinline__ void dp_pair_backward_kernel_body(const DpParams& p, 
             const int nn = T - 1 - it0 - FB - f;
             const bool ok = valid && nn > 0;
             enext[f] = (valid && nn >= 0) ? __ldg(pe - f * ldc) : 0.0f;
-            bnext[f] = ok ? __ldg(pb - f * ldc) : 0.0f;
-            gnext[f] = ok ? __ldg(pg - f * ldc) : 0.0f;
-            dnext[f] = (have && nn >= 1) ? __ldg(pd - f) : 0.0f;
+            bnext[f] = ok ? __ldcg(pb - f * ldc) : 0.0f;
+            gnext[f] = ok ? __ldcg(pg - f * ldc) : 0.0f;
+            dnext[f] = (have && nn >= 1) ? __ldcg(pd - f) : 0.0f;
         }
 #pragma unroll
         for (int f = 0; f < FB; ++f) {

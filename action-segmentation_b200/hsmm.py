@@ -171,7 +171,9 @@ def grouped_dp(mode, batches):
     launch per kernel family.  `batches`: list of dicts with the per-batch tensors of the single-batch entry points
     (em, C, init, trans, lenp, end, offset, lengths_i32, order, trans_list [, class_ids, want_labels, f64_state, grad,
     saved, out=(d_init, d_trans, d_len), d_em]).  Returns a list of per-batch results shaped like the single-batch
-    functions': mode 0 (spans, labels, None), mode 1 (logz, saved), mode 2 (d_init, d_trans, d_len, d_em)."""
+    functions': mode 0 (spans, labels, None), mode 1 (logz, saved), mode 2 (d_init, d_trans, d_len, d_em), mode 3
+    (forward and backward in one launch; needs trans_list, trans_list2 = successors, grad)
+    (logz, saved, d_init, d_trans, d_len, d_em)."""
     lib = _lib.load()
     n = len(batches)
     arr = (_lib.DpTask * n)()
@@ -203,6 +205,21 @@ def grouped_dp(mode, batches):
             logz = torch.empty(B, device=dev, dtype=torch.float64)
             t.out_logz, t.saved = _ptr(logz), _ptr(saved)
             results.append((logz, saved))
+        elif mode == 3:
+            saved = torch.empty(lib.hsmm_logz_saved_bytes(B, T, C, K, flags), device=dev, dtype=torch.uint8)
+            logz = torch.empty(B, device=dev, dtype=torch.float64)
+            if bt.get("out") is None:
+                d_init, d_trans, d_len = torch.zeros(C, device=dev), torch.zeros(C, C, device=dev), torch.zeros(K, C, device=dev)
+            else:
+                d_init, d_trans, d_len = bt["out"]
+            d_em = bt.get("d_em")
+            if d_em is None:
+                d_em = torch.empty(B, T, ldc, device=dev, dtype=torch.float32)
+            g = _f32(bt["grad"])
+            keep.append(g)
+            t.out_logz, t.saved, t.trans_list2 = _ptr(logz), _ptr(saved), _ptr(bt["trans_list2"])
+            t.grad_logz, t.d_init, t.d_trans, t.d_len, t.d_em = _ptr(g), _ptr(d_init), _ptr(d_trans), _ptr(d_len), _ptr(d_em)
+            results.append((logz, saved, d_init, d_trans, d_len, d_em))
         else:
             if bt.get("out") is None:
                 d_init, d_trans, d_len = torch.zeros(C, device=dev), torch.zeros(C, C, device=dev), torch.zeros(K, C, device=dev)

@@ -226,7 +226,7 @@ def packed_layout(tasks):
 
 
 def env_switches():
-    return {k: os.environ[k] for k in ("HSMM_BENCH_SKIP", "HSMM_BENCH_TASKS", "HSMM_BENCH_BUCKETS", "HSMM_BENCH_GROUPS", "HSMM_DISABLE_LIN", "HSMM_DISABLE_PAIR", "HSMM_PAIR_MIN_VIDEOS",
+    return {k: os.environ[k] for k in ("HSMM_BENCH_SKIP", "HSMM_BENCH_TASKS", "HSMM_BENCH_BUCKETS", "HSMM_BENCH_GROUPS", "HSMM_BENCH_FUSED", "HSMM_DISABLE_LIN", "HSMM_DISABLE_PAIR", "HSMM_PAIR_MIN_VIDEOS",
                                               "HSMM_FORCE_GENERIC") if os.environ.get(k)}
 
 
@@ -346,7 +346,7 @@ def grouped_eligible(tasks):
     return all(tk.chain and tk.K - 1 <= 20 and tk.C <= 32 for tk in tasks) and len({tk.penalty is not None for tk in tasks}) == 1
 
 
-def device_step_grouped(tasks, streams, packed, layout, world, reduce=True, n_groups=1):
+def device_step_grouped(tasks, streams, packed, layout, world, reduce=True, n_groups=1, fused=True):
     """The same work as `device_step`, with the DP kernels of several tasks in ONE launch per kernel family
     (hsmm_dp_grouped): per task emission scoring on the task's stream; per group of tasks {forward -> backward} on the
     group's stream and Viterbi on a second one; per task the class-weighted feature sums once its group's backward
@@ -390,9 +390,8 @@ def device_step_grouped(tasks, streams, packed, layout, world, reduce=True, n_gr
             for i, (spans, labels, _) in zip(idx, res):
                 outs[i] = (spans, labels, em_out[i][0], em_out[i][2])
         with torch.cuda.stream(s_dp):
-            fw = hsmm.grouped_dp(1, [dict(b, trans_list=tasks[i].pred) for b, i in zip(base, idx)])
-            bw_in = []
-            for b, i, (logz, saved) in zip(base, idx, fw):
+            fb_in = []
+            for b, i in zip(base, idx):
                 tk = tasks[i]
                 off, sizes = layout[i]
                 v, o = [], off
@@ -401,9 +400,15 @@ def device_step_grouped(tasks, streams, packed, layout, world, reduce=True, n_gr
                     o += m
                 wx, d_trans, d_len, d_init, wsum, lz = v
                 g = tk.gradw if world == 1 else tk.gradw / world
-                bw_in.append(dict(b, trans_list=tk.succ, saved=saved, grad=g,
+                fb_in.append(dict(b, trans_list=tk.pred, trans_list2=tk.succ, grad=g,
                                   out=(d_init, d_trans.view(tk.C, tk.C), d_len.view(tk.K, tk.C))))
-            bw = hsmm.grouped_dp(2, bw_in)
+            if fused:  # forward and backward of every video back to back in one launch
+                fb = hsmm.grouped_dp(3, fb_in)
+                fw = [(r[0], r[1]) for r in fb]
+                bw = [r[2:] for r in fb]
+            else:
+                fw = hsmm.grouped_dp(1, fb_in)
+                bw = hsmm.grouped_dp(2, [dict(b, trans_list=b["trans_list2"], saved=f[1]) for b, f in zip(fb_in, fw)])
             bwd_done = torch.cuda.Event()
             bwd_done.record(s_dp)
         for i, (logz, saved), (_, _, _, d_em) in zip(idx, fw, bw):
@@ -555,7 +560,7 @@ def kernel_breakdown(tasks, reps=3, decode_only=False):
     return {n: sum(v for (k, _), v in best.items() if k == n) for n in names}, launches
 
 
-def kernel_breakdown_grouped(tasks, reps=3):
+def kernel_breakdown_grouped(tasks, reps=3, fused=True):
     """As `kernel_breakdown` for the grouped step: emission and weighted sums per task, each DP pass as ONE grouped call."""
     from action_segmentation_b200 import hsmm
     best = {}
@@ -575,14 +580,19 @@ def kernel_breakdown_grouped(tasks, reps=3):
                                                                   params=tk.eparams)) for i, tk in enumerate(tasks)]
         base = [dict(em=e[0], C=tk.C, init=tk.init, trans=tk.trans, lenp=tk.lenp, end=tk.end, offset=e[2], lengths_i32=tk.lengths_i32,
                      order=tk.order, f64_state=xp) for tk, e in zip(tasks, ems)]
-        fw = timed(("logz_forward", 0), lambda: hsmm.grouped_dp(1, [dict(b, trans_list=tk.pred) for b, tk in zip(base, tasks)]))
-        bw = timed(("logz_backward", 0), lambda: hsmm.grouped_dp(2, [dict(b, trans_list=tk.succ, saved=f[1], grad=tk.gradw)
-                                                                      for b, tk, f in zip(base, tasks, fw)]))
+        if fused:
+            fb = timed(("logz_forward_backward", 0), lambda: hsmm.grouped_dp(3, [dict(b, trans_list=tk.pred, trans_list2=tk.succ,
+                                                                                      grad=tk.gradw) for b, tk in zip(base, tasks)]))
+            fw, bw = None, [r[2:] for r in fb]
+        else:
+            fw = timed(("logz_forward", 0), lambda: hsmm.grouped_dp(1, [dict(b, trans_list=tk.pred) for b, tk in zip(base, tasks)]))
+            bw = timed(("logz_backward", 0), lambda: hsmm.grouped_dp(2, [dict(b, trans_list=tk.succ, saved=f[1], grad=tk.gradw)
+                                                                          for b, tk, f in zip(base, tasks, fw)]))
         for i, (tk, r) in enumerate(zip(tasks, bw)):
             timed(("weighted_feature_sums", i), lambda: hsmm.weighted_feature_sums(tk.X, r[3], tk.C, tk.lengths_i32))
         timed(("viterbi", 0), lambda: hsmm.grouped_dp(0, [dict(b, trans_list=tk.pred, class_ids=tk.class_ids) for b, tk in zip(base, tasks)]))
         del fw, bw
-    names = ["emission", "logz_forward", "logz_backward", "weighted_feature_sums", "viterbi"]
+    names = ["emission"] + (["logz_forward_backward"] if fused else ["logz_forward", "logz_backward"]) + ["weighted_feature_sums", "viterbi"]
     kms = {n: sum(v for (k, _), v in best.items() if k == n) for n in names}
     launches = {n: sum(1 for (k, _) in best if k == n) for n in names}
     return kms, launches
@@ -817,12 +827,15 @@ def run_train_decode(args, cfg, rank, world, device, barrier, sampler):
     frames = sum(tk.frames for tk in tasks)
     layout, total = packed_layout(tasks)
     packed = torch.zeros(total, device=device)
-    n_groups = int(os.environ.get("HSMM_BENCH_GROUPS", "2"))
+    # forward + backward in one launch for the float-state kernels (the f64-state pair needs 172 registers: two launches,
+    # two half-groups so that one group's streaming kernels overlap the other's DP)
+    fused = os.environ.get("HSMM_BENCH_FUSED", "0" if cfg["narration"] else "1") == "1"
+    n_groups = int(os.environ.get("HSMM_BENCH_GROUPS", "1" if fused else "2"))
     grouped = n_groups > 0 and grouped_eligible(tasks) and len(tasks) > 1 and not os.environ.get("HSMM_BENCH_SKIP")
 
     def device_step(tasks, streams, packed, layout, world, reduce=True):  # noqa: F811 (the step of this run)
         if grouped:
-            return device_step_grouped(tasks, streams, packed, layout, world, reduce=reduce, n_groups=n_groups)
+            return device_step_grouped(tasks, streams, packed, layout, world, reduce=reduce, n_groups=n_groups, fused=fused)
         return globals()["device_step"](tasks, streams, packed, layout, world, reduce=reduce)
 
     streams = [torch.cuda.Stream() for _ in range(min(2 * len(tasks), 36) + 1 + 18 * int(os.environ.get("HSMM_BENCH_BUCKETS", "0")))]
@@ -912,11 +925,11 @@ def run_train_decode(args, cfg, rank, world, device, barrier, sampler):
 
     # ---- per-kernel durations and the roofline of the dominant kernel ---------------------------
     peak_gbs, peak_src = peak_hbm()
-    kms, klaunch = kernel_breakdown_grouped(tasks) if grouped else kernel_breakdown(tasks)
+    kms, klaunch = kernel_breakdown_grouped(tasks, fused=fused) if grouped else kernel_breakdown(tasks)
     dom = max(kms, key=kms.get)
     meanC = sum(tk.C * tk.frames for tk in tasks) / float(frames)
     pen_bytes = 4.0 * meanC if cfg["narration"] else 0.0
-    bpf = (4 * D + 8 + pen_bytes) if dom == "viterbi" else (8 * D + pen_bytes)
+    bpf = (4 * D + 8 + pen_bytes) if dom == "viterbi" else (8 * D + pen_bytes)  # decode / train step
     achieved = frames * bpf / (kms[dom] * 1e-3) / 1e9
     traffic = None
     try:
@@ -952,8 +965,9 @@ def run_train_decode(args, cfg, rank, world, device, barrier, sampler):
                    sum(tk.V for tk in tasks), "parallelism": "dp%d over videos, 1 packed all-reduce/step%s" % (
                        world, " on a side stream, overlapping the next step (double-buffered statistics)" if world > 1 and graph is not None else ""),
                    "launch": "eager (Python)" if graph is None else "CUDA-graph replay of the step (captured after eager warm-up)",
-                   "dp_launches": ("hsmm_dp_grouped: one launch per kernel family over the %d tasks (%d group%s)" % (
-                       len(tasks), n_groups, "" if n_groups == 1 else "s")) if grouped else "one launch per task and kernel family",
+                   "dp_launches": ("hsmm_dp_grouped: one launch per kernel family over the %d tasks (%d group%s%s)" % (
+                       len(tasks), n_groups, "" if n_groups == 1 else "s", "; forward + backward fused into one launch" if fused else ""))
+                   if grouped else "one launch per task and kernel family",
                    "l2_policy": "inputs larger than L2 (%.1f GB of features per step per GPU)" % (frames * D * 4 / 1e9),
                    "dp_variants": sorted(set("%s | %s | %s" % tuple(_lib.dp_variant(tk.C, tk.K, m, tk.chain, tk.penalty is not None)
                                                                     for m in (0, 1, 2)) for tk in tasks))},

@@ -149,9 +149,12 @@ int hsmm_logz_backward(const float* em, int ldc, const float* init, const float*
  * above once per batch launches kernels that each keep only a few dozen CTAs busy for as long as that batch's longest
  * video lasts.  Here one kernel per family covers all the batches (parameter blocks indexed by block id), which is what
  * fills a B200 when a whole split is decoded or a large step is taken.
- *   mode 0: hsmm_viterbi, 1: hsmm_logz_forward, 2: hsmm_logz_backward -- same semantics, same buffers per task.
- * Envelope: every task needs its sparse transition list (`trans_list` = predecessors for modes 0 and 1, successors for
- * mode 2), K - 1 <= 20, C <= 32, ldc = C rounded up to 4, and the same `flags` for all tasks; n <= 32 tasks per call.
+ *   mode 0: hsmm_viterbi, 1: hsmm_logz_forward, 2: hsmm_logz_backward -- same semantics, same buffers per task;
+ *   mode 3: forward AND backward in one launch (a video's backward pass starts as soon as its own forward pass ends;
+ *           grad_logz must be known up front, e.g. 1/B for the mean log-likelihood of semimarkov_modules.py:657).
+ * Envelope: every task needs its sparse transition list (`trans_list` = predecessors for modes 0, 1 and 3, successors for
+ * mode 2; `trans_list2` = successors for mode 3), K - 1 <= 20, C <= 32, ldc = C rounded up to 4, and the same `flags` for
+ * all tasks; n <= 32 tasks per call.
  * Outside the envelope the call returns HSMM_ERR_SHAPE and the caller uses the per-batch entry points.
  */
 typedef struct {
@@ -161,7 +164,8 @@ typedef struct {
     int B, Tmax, C, K, flags;
     int64_t* out_spans; int64_t* out_labels; double* out_score; void* workspace;   /* mode 0 */
     double* out_logz; void* saved;                                                   /* modes 1, 2 */
-    const float* grad_logz; float* d_init; float* d_trans; float* d_len; float* d_em; /* mode 2 */
+    const float* grad_logz; float* d_init; float* d_trans; float* d_len; float* d_em; /* modes 2, 3 */
+    const int32_t* trans_list2;                                                      /* mode 3: successors */
 } hsmm_dp_task;
 int hsmm_dp_grouped(int mode, int n, const hsmm_dp_task* tasks, void* stream);
 

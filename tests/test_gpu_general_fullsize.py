@@ -260,6 +260,12 @@ def test_grouped_launch_equals_per_batch_calls_and_oracle(f64_state, pair_mode):
             assert torch.allclose(a, b_, rtol=1e-5, atol=1e-5)  # C <= 16: the group runs <KR=20,S=1>, the batch <KR=10,S=2>
         check_against_oracle(prob, logz.cpu().numpy(), dict(E_init=d_init, E_trans=d_trans, E_len=d_len, E_em=d_em[:, :, :C]),
                              w.cpu().numpy().astype(np.float64))
+    # mode 3: forward and backward of every video back to back in ONE launch
+    fb = H.grouped_dp(3, [dict(b, trans_list=sp[0], trans_list2=sp[1], grad=w) for b, sp, w in zip(base, sps, ws)])
+    for (logz3, _, d_init3, d_trans3, d_len3, d_em3), (logz, _), (d_init, d_trans, d_len, d_em) in zip(fb, fw, bw):
+        assert torch.equal(logz3, logz)
+        for a, b_ in zip((d_init3, d_trans3, d_len3, d_em3), (d_init, d_trans, d_len, d_em)):
+            assert torch.allclose(a, b_, rtol=1e-5, atol=1e-6)
 
 
 def test_grouped_launch_rejects_shapes_outside_its_envelope():

@@ -8,11 +8,16 @@ KRE='regex:hsmm|etc::|wtc::|weighted_sums|dp_|emission|gen_|moments|gold|onehot'
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k "$KRE" -c 800 --csv --log-file $OUT/${TAG}_launches_cfg1.csv \
   python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-graph --no-sustained > $OUT/${TAG}_launches_cfg1.log 2>&1
 echo "launch list rc=$?"
+# 1b. --set full of the grouped DP kernels and the streaming kernels inside the bench step
+timeout 900 ncu --set full --clock-control none --import-source on -k "regex:_grouped|emission_tc|weighted_sums_tc" -s 40 -c 12 -o /tmp/${TAG}_step \
+  python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-graph --no-sustained > $OUT/${TAG}_ncu_step.log 2>&1
+echo "ncu step rc=$?"
+ncu -i /tmp/${TAG}_step.ncu-rep --page raw --csv > $OUT/${TAG}_ncu_step_raw.csv 2>/dev/null
 # 2. --set full of one task's kernels per config (summarised to CSV on the box; the .ncu-rep is too large to bring back)
-for spec in "1:23:20:2048" "2:23:20:2048" "0:11:100:512" "3:48:200:128" "3:48:500:64" "4:133:200:512" "4:64:100:1024"; do
-  IFS=: read cfg C K V <<< "$spec"
+for spec in "4:133:200:512:2:3" "4:64:100:1024:2:3" "4:16:50:2048:2:3"; do
+  IFS=: read cfg C K V SKIP CNT <<< "$spec"
   PROFILE_CONFIG=$cfg PROFILE_C=$C PROFILE_K=$K PROFILE_VIDEOS=$V timeout 900 ncu --set full --clock-control none --import-source on \
-    -k "$KRE" -s 8 -c 8 -o /tmp/${TAG}_cfg${cfg}_C${C}_K${K} python profiles/profile_one_task.py > $OUT/${TAG}_ncu_cfg${cfg}_C${C}_K${K}.log 2>&1
+    -k "$KRE" -s $SKIP -c $CNT -o /tmp/${TAG}_cfg${cfg}_C${C}_K${K} python profiles/profile_one_task.py > $OUT/${TAG}_ncu_cfg${cfg}_C${C}_K${K}.log 2>&1
   echo "ncu cfg$cfg C=$C K=$K rc=$?"
   ncu -i /tmp/${TAG}_cfg${cfg}_C${C}_K${K}.ncu-rep --page raw --csv > $OUT/${TAG}_ncu_cfg${cfg}_C${C}_K${K}_raw.csv 2>/dev/null
 done
