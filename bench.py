@@ -215,6 +215,14 @@ def make_workload(args, cfg, rank, device):
     return [make_task(C, cfg, gen, device) for C in classes]
 
 
+def step_weights(tk, world):
+    """d loss / d logZ_b of the step: 1 / (videos of the task over all ranks); built once, not inside the timed step."""
+    cache = tk.__dict__.setdefault("_gradw_world", {})
+    if world not in cache:
+        cache[world] = tk.gradw if world == 1 else (tk.gradw / world).contiguous()
+    return cache[world]
+
+
 def packed_layout(tasks):
     """Offsets of every task's [d_means | d_trans | d_len | d_init | sum logZ] slice of the packed buffer."""
     off, lay = 0, []
@@ -226,7 +234,7 @@ def packed_layout(tasks):
 
 
 def env_switches():
-    return {k: os.environ[k] for k in ("HSMM_BENCH_SKIP", "HSMM_BENCH_TASKS", "HSMM_BENCH_BUCKETS", "HSMM_BENCH_GROUPS", "HSMM_BENCH_FUSED", "HSMM_DISABLE_LIN", "HSMM_DISABLE_PAIR", "HSMM_PAIR_MIN_VIDEOS",
+    return {k: os.environ[k] for k in ("HSMM_BENCH_SKIP", "HSMM_BENCH_TASKS", "HSMM_BENCH_BUCKETS", "HSMM_BENCH_GROUPS", "HSMM_BENCH_FUSED", "HSMM_BENCH_NO_OVERLAP", "HSMM_BENCH_NO_REDUCE", "HSMM_DISABLE_LIN", "HSMM_DISABLE_PAIR", "HSMM_PAIR_MIN_VIDEOS",
                                               "HSMM_FORCE_GENERIC") if os.environ.get(k)}
 
 
@@ -284,7 +292,7 @@ def device_step(tasks, streams, packed, layout, world, reduce=True, decode_only=
         wx, d_trans, d_len, d_init, wsum, lz = v
         nb = int(os.environ.get("HSMM_BENCH_BUCKETS", "0"))
         xp = tk.penalty is not None
-        g = tk.gradw if world == 1 else tk.gradw / world
+        g = step_weights(tk, world)
         if nb > 1:
             # experiment: the task's forward/backward in nb length-homogeneous sub-batches, each its own chain
             ldc = em.shape[2]
@@ -399,7 +407,7 @@ def device_step_grouped(tasks, streams, packed, layout, world, reduce=True, n_gr
                     v.append(packed[o:o + m])
                     o += m
                 wx, d_trans, d_len, d_init, wsum, lz = v
-                g = tk.gradw if world == 1 else tk.gradw / world
+                g = step_weights(tk, world)
                 fb_in.append(dict(b, trans_list=tk.pred, trans_list2=tk.succ, grad=g,
                                   out=(d_init, d_trans.view(tk.C, tk.C), d_len.view(tk.K, tk.C))))
             if fused:  # forward and backward of every video back to back in one launch
@@ -857,7 +865,7 @@ def run_train_decode(args, cfg, rank, world, device, barrier, sampler):
             graph_outs = device_step(tasks, streams, packed, layout, world, reduce=False)  # noqa: F841 (kept alive)
         launches_per_step = _lib.launch_count() - l_cap
         graphs = [graph]
-        if world > 1:
+        if world > 1 and os.environ.get("HSMM_BENCH_NO_OVERLAP") != "1":
             # double-buffered statistics: step i's packed all-reduce runs on a side stream while step i+1's graph
             # (which accumulates into the OTHER buffer) already computes; a buffer is reused two steps later, after
             # its all-reduce has finished
@@ -880,7 +888,11 @@ def run_train_decode(args, cfg, rank, world, device, barrier, sampler):
         if i in pending:
             cur.wait_event(pending.pop(i))  # the buffer's previous all-reduce is done (it is zeroed by the graph)
         graphs[i].replay()
-        if world > 1:
+        if os.environ.get("HSMM_BENCH_NO_REDUCE") == "1":  # experiment: how much of the N > 1 step is the collective?
+            return
+        if world > 1 and comm is None:
+            torch.distributed.all_reduce(packs[i])
+        elif world > 1:
             done = torch.cuda.Event()
             done.record(cur)
             comm.wait_event(done)
@@ -904,9 +916,12 @@ def run_train_decode(args, cfg, rank, world, device, barrier, sampler):
     l0 = _lib.launch_count()
     ms = measure(one_step, args.steps, barrier, drain)
     launches = (_lib.launch_count() - l0) if graph is None else launches_per_step * args.steps
+    ms_own = ms
     ms, frames_all = reduce_timing(ms, frames, world, device)
     ms_per_step = ms / args.steps
     value = frames_all / (ms_per_step * 1e-3)
+    if world > 1 and os.environ.get("HSMM_BENCH_VERBOSE"):
+        print("rank %d: %.3f ms/step on %d frames" % (rank, ms_own / args.steps, frames), file=sys.stderr)
 
     # ---- sustained: the same step back to back for >= 2 s (the DP kernels are issue-bound and follow the SM clock) ----
     sustained = None
@@ -963,7 +978,7 @@ def run_train_decode(args, cfg, rank, world, device, barrier, sampler):
         "data": "synthetic",
         "config": {"workload": workload_name(args, cfg), "frames_per_step_per_gpu": frames, "videos_per_step_per_gpu":
                    sum(tk.V for tk in tasks), "parallelism": "dp%d over videos, 1 packed all-reduce/step%s" % (
-                       world, " on a side stream, overlapping the next step (double-buffered statistics)" if world > 1 and graph is not None else ""),
+                       world, " on a side stream, overlapping the next step (double-buffered statistics)" if comm is not None else ""),
                    "launch": "eager (Python)" if graph is None else "CUDA-graph replay of the step (captured after eager warm-up)",
                    "dp_launches": ("hsmm_dp_grouped: one launch per kernel family over the %d tasks (%d group%s%s)" % (
                        len(tasks), n_groups, "" if n_groups == 1 else "s", "; forward + backward fused into one launch" if fused else ""))
@@ -1115,7 +1130,7 @@ def main():
         sw = env_switches()
         if sw:
             result["config"]["env_switches"] = sw
-            if "HSMM_BENCH_SKIP" in sw or "HSMM_BENCH_TASKS" in sw:
+            if "HSMM_BENCH_SKIP" in sw or "HSMM_BENCH_TASKS" in sw or "HSMM_BENCH_NO_REDUCE" in sw:
                 result["invalid"] = "ablation run: HSMM_BENCH_SKIP / HSMM_BENCH_TASKS drop work from the timed region"
         print(json.dumps(result))
     if world > 1:
