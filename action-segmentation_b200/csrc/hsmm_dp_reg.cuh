@@ -966,23 +966,42 @@ static RegChoice choose(int C, int L, int mode, bool sparse, bool xp = false) {
 }
 
 // MODE: 0 Viterbi, 1 log-semiring forward, 2 backward.  XP: extended-precision per-class state.
+static int dp_num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+            n = 148;
+    }
+    return n;
+}
+
 template <int MODE, bool XP, int KR, int S, int TM, bool LREG, int MAXT>
-static int launch_one(const DpParams& p, const RegChoice& ch, cudaStream_t st) {
-    const int blocks = (p.B + ch.VPB - 1) / ch.VPB;
-    const int threads = ch.VPB * ch.W * 32;
+static int launch_one(const DpParams& p0, const RegChoice& ch, cudaStream_t st) {
+    // videos per CTA: as many as the thread budget allows for big batches, fewer when that would leave SMs without a
+    // CTA (512 videos at 8 per CTA are 64 CTAs on a 148-SM part: configs[0])
+    DpParams p = p0;
+    int vpb = ch.VPB;
+    const int want = 2 * dp_num_sms();
+    while (vpb > 1 && (p.B + vpb - 1) / vpb < want) --vpb;
+    p.VPB = vpb;
+    const RegVariant rv{KR, S, LREG};
+    const size_t smem = (vpb == ch.VPB) ? ch.smem : smem_bytes(rv, p.C, ch.W, vpb, TM, MODE, XP);
+    const int blocks = (p.B + vpb - 1) / vpb;
+    const int threads = vpb * ch.W * 32;
     cudaError_t e = cudaSuccess;
     if constexpr (MODE == 0) {
         auto k = dp_forward_kernel<true, false, KR, S, TM, LREG, MAXT>;
-        if (ch.smem > 48 * 1024) e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ch.smem);
-        if (e == cudaSuccess) k<<<blocks, threads, ch.smem, st>>>(p);
+        if (smem > 48 * 1024) e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) k<<<blocks, threads, smem, st>>>(p);
     } else if constexpr (MODE == 1) {
         auto k = dp_forward_kernel<false, XP, KR, S, TM, LREG, MAXT>;
-        if (ch.smem > 48 * 1024) e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ch.smem);
-        if (e == cudaSuccess) k<<<blocks, threads, ch.smem, st>>>(p);
+        if (smem > 48 * 1024) e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) k<<<blocks, threads, smem, st>>>(p);
     } else {
         auto k = dp_backward_kernel<XP, KR, S, TM, LREG, MAXT>;
-        if (ch.smem > 48 * 1024) e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ch.smem);
-        if (e == cudaSuccess) k<<<blocks, threads, ch.smem, st>>>(p);
+        if (smem > 48 * 1024) e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) k<<<blocks, threads, smem, st>>>(p);
     }
     if (e != cudaSuccess) {
         set_error("cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
