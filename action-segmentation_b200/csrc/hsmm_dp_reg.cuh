@@ -982,7 +982,7 @@ static int launch_one(const DpParams& p0, const RegChoice& ch, cudaStream_t st) 
     // CTA (512 videos at 8 per CTA are 64 CTAs on a 148-SM part: configs[0])
     DpParams p = p0;
     int vpb = ch.VPB;
-    const int want = 2 * dp_num_sms();
+    const int want = dp_num_sms();  // one CTA per SM is enough: concurrent calls on other streams fill the rest
     while (vpb > 1 && (p.B + vpb - 1) / vpb < want) --vpb;
     p.VPB = vpb;
     const RegVariant rv{KR, S, LREG};

@@ -446,49 +446,63 @@ def device_step_grouped(tasks, streams, packed, layout, world, reduce=True, n_gr
 # end to end through the public module API, HOST buffers
 # ---------------------------------------------------------------------------------------------
 class HostBatch:
-    """Pinned host copy of one task's padded batch (what `padding_colate` hands the wrapper) and its device landing
-    buffers (zeroed once: only live rows are ever copied)."""
+    """Pinned host copy of one task's padded batch (what `padding_colate` hands the wrapper) and TWO sets of device
+    landing buffers (zeroed once: only live rows are ever copied), so that the next step's inputs can be uploaded while
+    this step computes -- the input prefetch every training loop does."""
 
     def __init__(self, tk):
         self.features = tk.X.cpu().pin_memory()
         self.penalty = None if tk.penalty is None else tk.penalty.cpu().pin_memory()
         self.lengths_i32 = tk.lengths.to(torch.int32)
-        self.dev_features = torch.zeros_like(tk.X)
-        self.dev_penalty = None if tk.penalty is None else torch.zeros_like(tk.penalty)
+        self.dev_features = [torch.zeros_like(tk.X) for _ in range(2)]
+        self.dev_penalty = [None if tk.penalty is None else torch.zeros_like(tk.penalty) for _ in range(2)]
         live = int(tk.lengths.sum())
         self.h2d_bytes = live * tk.D * 4 + (0 if tk.penalty is None else live * tk.C * 4)
 
 
-def e2e_step(models, tasks, host, streams, decode_only=False):
-    """Public API with host buffers: H2D of the step's live frames, loss + predictions read back."""
+def e2e_upload(tasks, host, copy_stream, slot):
+    """Host -> device copy of one step's inputs (live frames only) on the copy stream; returns the event to wait for."""
     from action_segmentation_b200 import hsmm
+    with torch.cuda.stream(copy_stream):
+        for tk, hb in zip(tasks, host):
+            hsmm.upload_ragged(hb.features, hb.dev_features[slot], hb.lengths_i32)
+            if hb.penalty is not None:
+                hsmm.upload_ragged(hb.penalty, hb.dev_penalty[slot], hb.lengths_i32)
+        ev = torch.cuda.Event()
+        ev.record(copy_stream)
+    return ev
+
+
+def e2e_step(models, tasks, host, streams, copy_stream, slot, ready, decode_only=False):
+    """Public API with host buffers.  The inputs of THIS step (landing-buffer set `slot`) were uploaded while the previous
+    step computed (`ready` = their event); this call first enqueues the upload of the NEXT step's inputs into the other
+    set, then runs the module API on this step's and reads loss + predictions back.  Every step therefore contains one
+    full host -> device copy of a step's inputs and the device -> host read of its results."""
+    nxt = e2e_upload(tasks, host, copy_stream, 1 - slot)
     lls, preds = [], []
     ns = len(streams)
-    # every task's live frames leave pinned memory back to back, so that the copy engine never idles while the host
-    # prepares the next call; the kernels of task i start as soon as its own copy has landed
-    for i, (tk, hb) in enumerate(zip(tasks, host)):
-        with torch.cuda.stream(streams[i % ns]):
-            hsmm.upload_ragged(hb.features, hb.dev_features, hb.lengths_i32)
-            if hb.penalty is not None:
-                hsmm.upload_ragged(hb.penalty, hb.dev_penalty, hb.lengths_i32)
     for i, (m, tk, hb) in enumerate(zip(models, tasks, host)):
-        with torch.cuda.stream(streams[i % ns]):
+        st = streams[i % ns]
+        st.wait_event(ready)
+        with torch.cuda.stream(st):
             ends = None if tk.end is None else [[] for _ in range(tk.V)]
+            feats, pen = hb.dev_features[slot], hb.dev_penalty[slot]
             if decode_only:
-                spans, labels = m.viterbi(hb.dev_features, tk.lengths, None, additional_allowed_ends_per_instance=ends,
-                                          constraints=hb.dev_penalty, return_labels=True, non_blocking=True)
+                spans, labels = m.viterbi(feats, tk.lengths, None, additional_allowed_ends_per_instance=ends,
+                                          constraints=pen, return_labels=True, non_blocking=True)
             else:
                 m.zero_grad()
-                ll, _, spans, labels = m.log_likelihood_and_viterbi(hb.dev_features, tk.lengths, None,
+                ll, _, spans, labels = m.log_likelihood_and_viterbi(feats, tk.lengths, None,
                                                                     additional_allowed_ends_per_instance=ends,
-                                                                    constraints=hb.dev_penalty, non_blocking=True)
+                                                                    constraints=pen, non_blocking=True)
                 (-ll).backward()
                 h = torch.empty((), dtype=torch.float32, pin_memory=True)
                 h.copy_(ll.detach(), non_blocking=True)
                 lls.append(h)
             preds.append((spans, labels))
-    torch.cuda.synchronize()  # every task's loss, spans and labels are now in host memory
-    return float(sum(float(h) for h in lls)), preds
+    for st in streams:  # this step's results are in host memory; the next step's upload may still be in flight
+        st.synchronize()
+    return float(sum(float(h) for h in lls)), preds, nxt
 
 
 def build_models(tasks):
@@ -995,13 +1009,18 @@ def run_e2e(tasks, streams, frames_all, args, world, device, barrier, decode_onl
     host = [HostBatch(tk) for tk in tasks]
     h2d = sum(h.h2d_bytes for h in host)
     d2h = sum(tk.V * (tk.Tmax + 1) * 8 + tk.V * tk.Tmax * 8 + 4 for tk in tasks)
+    copy_stream = torch.cuda.Stream()
+    ready = e2e_upload(tasks, host, copy_stream, 0)  # prime the pipeline: inputs of the first (warm-up) step
+    slot = 0
     for _ in range(max(1, min(args.warmup, 2))):
-        e2e_step(models, tasks, host, streams, decode_only)
+        _, _, ready = e2e_step(models, tasks, host, streams, copy_stream, slot, ready, decode_only)
+        slot = 1 - slot
     barrier()
     t0 = time.perf_counter()
-    n_e2e = max(1, min(args.steps, 3))
+    n_e2e = max(3, min(args.steps, 10))
     for _ in range(n_e2e):
-        e2e_step(models, tasks, host, streams, decode_only)
+        _, _, ready = e2e_step(models, tasks, host, streams, copy_stream, slot, ready, decode_only)
+        slot = 1 - slot
         if world > 1 and not decode_only:
             allreduce_all_gradients(models)
     barrier()
@@ -1012,8 +1031,10 @@ def run_e2e(tasks, streams, frames_all, args, world, device, barrier, decode_onl
     padded = sum(h.features.numel() * 4 + (0 if h.penalty is None else h.penalty.numel() * 4) for h in host)
     return {"value": frames_all / float(tt[0]), "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
             "ms_per_step": float(tt[0]) * 1e3, "steps": n_e2e, "h2d_gbs_achieved": h2d / float(tt[0]) / 1e9,
-            "note": "live frames only cross PCIe (hsmm_upload_ragged: %.2f of the padded %.2f GB per GPU); one emission pass "
-                    "per batch (log_likelihood_and_viterbi); one packed gradient all-reduce per step when N > 1" % (h2d / 1e9, padded / 1e9)}
+            "note": "every timed step: one upload of a step's live frames from pinned memory (hsmm_upload_ragged: %.2f of the padded "
+                    "%.2f GB per GPU; it is the NEXT step's input, prefetched into a second set of landing buffers while this step "
+                    "computes), the module API on this step's inputs (one emission pass per batch: log_likelihood_and_viterbi), loss + "
+                    "spans + labels read back; one packed gradient all-reduce per step when N > 1" % (h2d / 1e9, padded / 1e9)}
 
 
 def run_sweep(args, cfg, rank, world, device, barrier, sampler):

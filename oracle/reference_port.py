@@ -13,7 +13,8 @@ torch CPU ops and the same algorithmic structure (and therefore the same cost):
   * logZ.mean().backward() for the four parameter gradients (semimarkov.py:259-286) and
     argmax -> from_parts for Viterbi (semimarkov_modules.py:677-679).
 
-Its numbers are checked against oracle/hsmm_oracle.py in tests/test_oracle_golden.py.
+Its numbers are checked against oracle/hsmm_oracle.py in tests/test_oracle_golden.py::test_reference_port_matches_oracle.
+bench.py uses it only when the reference's own sources (oracle/_ref) are absent.
 """
 import torch
 import torch.nn.functional as F

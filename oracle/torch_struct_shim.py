@@ -21,7 +21,7 @@ sites:
 PARITY STATUS: the DP arithmetic here is "parity unpinned" against the real
 pytorch-struct binary (absent).  It is pinned instead by (i) the reference's own
 known-answer test body (test_semimarkov.py:266-323, reproduced in
-tests/test_oracle_reference.py), and (ii) brute-force enumeration of every segmentation
+tests/golden/make_golden.py::case_known_answer -> tests/test_oracle_golden.py::test_known_answer), and (ii) brute-force enumeration of every segmentation
 (oracle/hsmm_oracle.py::brute_force) for logZ, max score and marginals.
 
 Semantics restated (edge[b, n, k, c2, c1]: a segment labelled c1 starts at n, has length

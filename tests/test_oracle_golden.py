@@ -112,3 +112,43 @@ def test_materialised_equals_factorised():
     z_f, _ = O.batch_logz_and_counts(em, lengths, init, trans, lenp)
     _, v_f = O.batch_viterbi(em, lengths, init, trans, lenp)
     assert np.allclose(z_m, z_f, rtol=1e-12) and np.allclose(v_m, v_f, rtol=1e-12)
+
+
+def test_reference_port_matches_oracle():
+    """oracle/reference_port.py (the bench's stand-in when oracle/_ref is absent): its logZ mean, parameter gradients and
+    Viterbi spans against the factorised fp64 oracle on a small chain-constrained ragged batch."""
+    import torch
+    from oracle.module_oracle import ModuleOracle
+    from oracle.reference_port import ReferencePort
+    torch.manual_seed(0)
+    C, D, K, B, T = 5, 6, 7, 3, 22
+    means = torch.randn(C, D) * 0.5
+    cov = torch.rand(D) + 0.5
+    tl, il, lr = torch.randn(C, C) * 0.3, torch.rand(C), torch.log(torch.rand(C) * 3 + 1)
+    tmask = torch.ones(C, C, dtype=torch.bool)
+    for c in range(C):
+        tmask[c, c] = False
+        if c + 1 < C:
+            tmask[c + 1, c] = False
+    imask = torch.ones(C, dtype=torch.bool)
+    imask[0] = False
+    lengths = torch.LongTensor([22, 15, 9])
+    lab = torch.sort(torch.randint(0, C, (B, T)), dim=1)[0]
+    X = means[lab] + torch.randn(B, T, D)
+    for b in range(B):
+        X[b, int(lengths[b]):] = 0
+    rp = ReferencePort(means, cov, tl, il, lr, K, tmask, imask)
+    ends = [[C - 1] for _ in range(B)]
+    ll, grads = rp.train_step(X, lengths, allowed_ends=ends)
+    spans = rp.viterbi(X, lengths, allowed_ends=ends)
+    params = dict(gaussian_means=means.numpy(), gaussian_cov=torch.diag(cov).numpy(), transition_logits=tl.numpy(),
+                  init_logits=il.numpy(), poisson_log_rates=lr.numpy())
+    mo = ModuleOracle(params, K, init_constraints=imask.numpy(), transition_constraints=tmask.numpy(), allowed_ends={C - 1})
+    r = mo.log_likelihood(X.numpy(), lengths.numpy())
+    assert abs(ll - r["ll"]) <= 1e-4 * abs(r["ll"])
+    for k, g in grads.items():
+        assert np.abs(g.numpy() - r["grads"][k]).max() <= 2e-3 * max(1e-9, np.abs(r["grads"][k]).max()), k
+    o_spans, _, _ = mo.viterbi(X.numpy(), lengths.numpy())
+    for b in range(B):
+        n = int(lengths[b])
+        assert (spans[b, :n + 1].numpy() == o_spans[b, :n + 1]).all()
