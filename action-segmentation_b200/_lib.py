@@ -10,7 +10,7 @@ LIB_PATH = os.path.join(HERE, "libhsmm_b200.so")
 EXPORTS = [
     "hsmm_version", "hsmm_last_error", "hsmm_emission", "hsmm_emission_workspace_bytes", "hsmm_viterbi_workspace_bytes", "hsmm_logz_saved_bytes",
     "hsmm_viterbi", "hsmm_logz_forward", "hsmm_logz_backward", "hsmm_weighted_feature_sums", "hsmm_gold_score",
-    "hsmm_feature_moments", "hsmm_onehot_weights", "hsmm_dp_variant", "hsmm_launch_count", "hsmm_set_linear_window", "hsmm_set_generic_dp", "hsmm_upload_ragged", "hsmm_dp_grouped", "hsmm_set_pair_min_videos",
+    "hsmm_feature_moments", "hsmm_onehot_weights", "hsmm_dp_variant", "hsmm_launch_count", "hsmm_set_linear_window", "hsmm_set_generic_dp", "hsmm_upload_ragged", "hsmm_upload_ragged_mapped", "hsmm_dp_grouped", "hsmm_set_pair_min_videos",
 ]
 
 _lib = None
@@ -67,6 +67,8 @@ def load():
     lib.hsmm_onehot_weights.argtypes = [p, p, i, i, i, i, p, p]
     lib.hsmm_upload_ragged.argtypes = [p, p, p, i, i, i, p]
     lib.hsmm_upload_ragged.restype = i
+    lib.hsmm_upload_ragged_mapped.argtypes = [p, p, p, i, i, i, p]
+    lib.hsmm_upload_ragged_mapped.restype = i
     lib.hsmm_dp_grouped.argtypes = [i, i, ctypes.POINTER(DpTask), p]
     lib.hsmm_dp_grouped.restype = i
     lib.hsmm_set_pair_min_videos.argtypes = [i]

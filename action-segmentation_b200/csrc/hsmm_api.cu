@@ -81,6 +81,7 @@ static bool may_use_gen(int C, int L, bool logz, bool xp) {
 static size_t align256(size_t n) { return (n + 255) / 256 * 256; }
 int launch_emission(const float*, const float*, const float*, const float*, const float*, const float*, const int32_t*, int, int, int,
                     int, int, float*, float*, double*, cudaStream_t);
+int launch_upload_ragged(const float*, float*, const int32_t*, int, int, int, int, cudaStream_t);
 size_t emission_tc_workspace_bytes(int D, int C);
 int launch_emission_tc(const float*, const float*, const float*, const float*, const float*, const float*, const int32_t*, int, int,
                        int, int, int, float*, float*, double*, void*, int, cudaStream_t);
@@ -439,6 +440,33 @@ int hsmm_upload_ragged(const float* host, float* dev, const int32_t* lengths_hos
         b = e;
     }
     return HSMM_OK;
+}
+
+int hsmm_upload_ragged_mapped(const float* host, float* dev, const int32_t* lengths, int B, int Tmax, int width, void* stream) {
+    if (!host || !dev || !lengths) {
+        set_error("hsmm_upload_ragged_mapped: null pointer");
+        return HSMM_ERR_ARG;
+    }
+    if (B <= 0 || Tmax <= 0 || width <= 0 || width % 4 != 0) {
+        set_error("hsmm_upload_ragged_mapped: bad shape B=%d Tmax=%d width=%d (width must be a multiple of 4)", B, Tmax, width);
+        return HSMM_ERR_SHAPE;
+    }
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, host) != cudaSuccess || at.type != cudaMemoryTypeHost || !at.devicePointer) {
+        cudaGetLastError();
+        set_error("hsmm_upload_ragged_mapped: host is not pinned memory the device can address (use hsmm_upload_ragged)");
+        return HSMM_ERR_ARG;
+    }
+    if ((reinterpret_cast<uintptr_t>(at.devicePointer) & 15) || (reinterpret_cast<uintptr_t>(dev) & 15)) {
+        set_error("hsmm_upload_ragged_mapped: buffers must be 16-byte aligned");
+        return HSMM_ERR_ARG;
+    }
+    // 96 CTAs x 512 threads x 2 loads of 16 B = 1.5 MB in flight (r02q, configs[1] e2e: 8 CTAs 46.5, 24 CTAs 46.7, 48 CTAs
+    // 47.1, 96 CTAs 47.8 GB/s; the per-video copy-engine path 44.8 GB/s); they use ~10 K registers each and leave the rest
+    // of the SMs to the step that computes meanwhile
+    static const int ctas = [] { const char* e = getenv("HSMM_UPLOAD_CTAS"); return e && atoi(e) > 0 ? atoi(e) : 96; }();
+    return launch_upload_ragged(reinterpret_cast<const float*>(at.devicePointer), dev, lengths, B, Tmax, width, ctas,
+                                (cudaStream_t)stream);
 }
 
 int hsmm_onehot_weights(const int32_t* labels, const int32_t* lengths, int B, int Tmax, int C, int ldc, float* weights,

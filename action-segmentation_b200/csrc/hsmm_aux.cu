@@ -392,7 +392,8 @@ int launch_weighted_sums_tc(const float* X, const float* wgt, int ldc, const int
 int launch_weighted_sums(const float* X, const float* wgt, int ldc, const int32_t* lengths, int B, int Tmax, int D, int C,
                          float* out_wx, float* out_wsum, int num_sms, cudaStream_t st) {
     {
-        // tensor-core path for the shapes it takes (D <= 224, C <= 32, aligned); 1 = not eligible -> SIMT kernels below
+        // tensor-core path for the shapes it takes (aligned, D <= 896 in feature blocks of 224, C <= 96 in class blocks of
+        // 32: one launch per block pair); 1 = not eligible -> SIMT kernels below
         const int rc = launch_weighted_sums_tc(X, wgt, ldc, lengths, B, Tmax, D, C, out_wx, out_wsum, num_sms, st);
         if (rc != 1) return rc;
     }
@@ -477,6 +478,50 @@ __global__ void onehot_kernel(const int32_t* __restrict__ labels, const int32_t*
         const int t = (int)(bt % Tmax), b = (int)(bt / Tmax);
         out[i] = (t < lengths[b] && c < C && labels[bt] == c) ? 1.0f : 0.0f;
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Ragged upload by the SMs: live rows of a padded batch in MAPPED pinned host memory -> device buffer
+// ---------------------------------------------------------------------------------------------
+// One copy-engine transfer per video costs ~3.8 us of set-up (a 1 MB cudaMemcpyAsync reaches 45 GB/s where a 1 GB one
+// reaches 55 GB/s on this box); a few CTAs reading the host rows over PCIe with 16-byte loads pay it once.  Work item =
+// (video, 16 KB piece) over the PADDED index space, pieces behind the end of a video are skipped.
+constexpr int UP_PIECE = 1024;  // uint4 per piece (16 KB)
+constexpr int UP_THREADS = 512;
+__global__ void __launch_bounds__(UP_THREADS) upload_ragged_kernel(const uint4* __restrict__ host, uint4* __restrict__ dev,
+                                                                  const int32_t* __restrict__ lengths, int B, int Tmax,
+                                                                  long long row_q /* uint4 per row */) {
+    const long long vid_q = (long long)Tmax * row_q;
+    const long long ppv = (vid_q + UP_PIECE - 1) / UP_PIECE;
+    const long long items = (long long)B * ppv;
+    for (long long it = blockIdx.x; it < items; it += gridDim.x) {
+        const int b = (int)(it / ppv);
+        const long long q0 = (it - (long long)b * ppv) * UP_PIECE;
+        const long long live = (long long)min(max(lengths[b], 0), Tmax) * row_q;
+        if (q0 >= live) continue;
+        const long long n = min((long long)UP_PIECE, live - q0);
+        const uint4* src = host + (long long)b * vid_q + q0;
+        uint4* dst = dev + (long long)b * vid_q + q0;
+        // UP_PIECE / UP_THREADS = 2 independent loads per thread in flight
+        uint4 v[UP_PIECE / UP_THREADS];
+#pragma unroll
+        for (int k = 0; k < UP_PIECE / UP_THREADS; ++k) {
+            const int i = threadIdx.x + k * UP_THREADS;
+            if (i < n) v[k] = __ldcs(src + i);
+        }
+#pragma unroll
+        for (int k = 0; k < UP_PIECE / UP_THREADS; ++k) {
+            const int i = threadIdx.x + k * UP_THREADS;
+            if (i < n) dst[i] = v[k];
+        }
+    }
+}
+
+int launch_upload_ragged(const float* host_mapped, float* dev, const int32_t* lengths, int B, int Tmax, int width, int ctas,
+                         cudaStream_t st) {
+    upload_ragged_kernel<<<ctas, UP_THREADS, 0, st>>>(reinterpret_cast<const uint4*>(host_mapped), reinterpret_cast<uint4*>(dev),
+                                                     lengths, B, Tmax, (long long)width / 4);
+    return check_launch("upload_ragged_kernel");
 }
 
 int launch_onehot(const int32_t* labels, const int32_t* lengths, int B, int Tmax, int C, int ldc, float* out, int num_sms,

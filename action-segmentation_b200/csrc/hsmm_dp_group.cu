@@ -21,8 +21,8 @@ bool dp_pair_enabled_for(int videos);
 // long videos are still going forward (the saved planes it reads back were written by the same warp: L2-coherent loads).
 // A video the forward pass flags (fflag) is skipped by the backward body and left, with its backward pass, to the
 // log-domain kernels launched behind.
-template <bool XP>
-__global__ void __launch_bounds__(128, XP ? 1 : 4) dp_lin_fb_kernel_grouped(const __grid_constant__ DpGroup g) {
+template <bool XP, int MINB>
+__global__ void __launch_bounds__(128, MINB) dp_lin_fb_kernel_grouped(const __grid_constant__ DpGroup g) {
     int local;
     const int t = group_find(g, blockIdx.x, local);
     dp_lin_forward_kernel_body<XP, 20, 1, 2>(g.t[t], local);
@@ -67,9 +67,13 @@ static int launch_generic(DpGroup& g, int blocks, int mode, size_t smem, cudaStr
 template <bool XP>
 static int launch_lin_group(DpGroup& g, int blocks, int mode, cudaStream_t st) {
     const size_t smem = 4 * (2 * 32 + 2) * sizeof(float);
-    if (mode == 3)
-        dp_lin_fb_kernel_grouped<XP><<<blocks, 128, smem, st>>>(g);
-    else if (mode == 0)
+    if (mode == 3) {
+        // 4 CTAs per SM for the float-state pair (128 registers); forcing 5 spills the windows and doubles the time (r02p A/B)
+        if constexpr (XP)
+            dp_lin_fb_kernel_grouped<XP, 1><<<blocks, 128, smem, st>>>(g);
+        else
+            dp_lin_fb_kernel_grouped<false, 4><<<blocks, 128, smem, st>>>(g);
+    } else if (mode == 0)
         dp_vit2_kernel_grouped<20, 1, 2><<<blocks, 128, smem, st>>>(g);
     else if (mode == 1)
         dp_lin_forward_kernel_grouped<XP, 20, 1, 2><<<blocks, 128, smem, st>>>(g);

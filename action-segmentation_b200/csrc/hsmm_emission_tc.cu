@@ -49,12 +49,16 @@ struct Params {
     double* offset;
     const float* row_const;  // device scalar
     int B, Tmax, D, C, ldc;
+    int wcols;    // columns of em this launch writes (a multiple of 4; == ldc unless `raw`)
+    int raw;      // class-block passes for C > 64: 0 = the whole class set in one launch; 1 / 2 = first / later block of
+                  // <= 64 classes: em gets the UNSHIFTED scores of the block's columns, rowterm (first block only) the
+                  // class-independent term, offset nothing -- emission_finish_kernel shifts the rows afterwards
     int npad;     // classes padded to a multiple of 16 (UMMA N)
     int nchunk;   // ceil(D / 32)
     int nstage;   // ring depth
 };
 
-template <int NB>  // NPAD = 16 * NB
+template <int NB, bool HALF>  // NPAD = 16 * NB; HALF: 256 TMEM columns (NB <= 2, at most 4 stages), so that two CTAs share an SM
 // (THREADS, 2): caps the kernel at 96 registers -- 30 K registers per CTA, so that two CTAs of the DP kernels (12-16 K
 // registers each) stay resident beside it and use the issue slots this HBM-bound kernel leaves idle
 __global__ void __launch_bounds__(THREADS, 2)
@@ -64,7 +68,9 @@ emission_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
     // small class weights sit behind each other in shared memory, so xb meets both in ONE MMA with N = 2 NPAD: two MMAs
     // per k-step instead of three); the epilogue adds the two halves.  Two accumulators (double buffer).
     constexpr int ACC_STRIDE = 2 * NPAD;
-    constexpr int TMEM_COLS = 512;   // accumulators in [0, 4 NPAD) <= 256, xs slots behind XS_BASE
+    constexpr int TMEM_COLS = HALF ? 256 : 512;   // accumulators in [0, 4 NPAD), xs slots behind XSB
+    constexpr int XSB = HALF ? XS_BASE / 2 : XS_BASE;
+    static_assert(!HALF || NB <= 2, "256 TMEM columns: accumulators must end at column 128");
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // carve: [W: nchunk x (big NPAD x 128 B, small NPAD x 128 B)] [stages] [bias NPAD] [inv_var nchunk*32] [barriers]
     // (offset arithmetic on the __shared__ symbol keeps the address space visible to the compiler: LDS/STS, not generic LD/ST)
@@ -171,7 +177,7 @@ emission_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
                 mbar_wait(conv + st, ph);
                 tc_fence_after();
                 const uint64_t xb = desc_at(desc0, st0 + st * STAGE_BYTES);
-                const uint32_t xs = tmem_base + XS_BASE + st * KC;   // 128 lanes x 32 columns of remainders
+                const uint32_t xs = tmem_base + XSB + st * KC;   // 128 lanes x 32 columns of remainders
                 const uint64_t wb = desc_at(desc0, w0 + ch * w_chunk_bytes);   // NPAD rows big, then NPAD rows small
                 const int ksteps = (ch == p.nchunk - 1) ? klast : 4;
 #pragma unroll
@@ -231,7 +237,7 @@ emission_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
                     sm[4 * lj + 3] = x[lj].w - __uint_as_float(__float_as_uint(x[lj].w) & TF32_MASK);
                 }
                 rowsq += q0 + q1;
-                tc_st32(tmem_base + ((uint32_t)(q * 32) << 16) + XS_BASE + st * KC, sm);
+                tc_st32(tmem_base + ((uint32_t)(q * 32) << 16) + XSB + st * KC, sm);
                 tc_wait_st();
                 tc_fence_before();
                 mbar_arrive(conv + st);
@@ -271,8 +277,8 @@ emission_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
                 const int len = max(p.lengths[b], 0);
                 if (t < (len + TILE_M - 1) / TILE_M * TILE_M) continue;
                 float* em_r = p.em + (size_t)row * p.ldc;
-                for (int c4 = 0; c4 * 4 < p.ldc; ++c4) *reinterpret_cast<float4*>(em_r + c4 * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
-                p.rowterm[row] = 0.0f;
+                for (int c4 = 0; c4 * 4 < p.wcols; ++c4) *reinterpret_cast<float4*>(em_r + c4 * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (p.raw < 2) p.rowterm[row] = 0.0f;
             }
         }
 
@@ -305,7 +311,11 @@ emission_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
             if (in_range) {
                 float* em_r = p.em + (size_t)row * p.ldc;
                 float rt = 0.0f;
-                if (live) {
+                if (live && p.raw) {
+#pragma unroll
+                    for (int c = 0; c < NPAD; ++c) v[c] = (c < p.C) ? v[c] + bias_s[c] : 0.0f;
+                    rt = -0.5f * rowsq + row_const;
+                } else if (live) {
                     const float* pen_r = p.penalty ? p.penalty + (size_t)row * p.C : nullptr;
                     float m = NEG;
 #pragma unroll
@@ -333,9 +343,9 @@ emission_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
                 }
 #pragma unroll
                 for (int c4 = 0; c4 < NPAD / 4; ++c4)
-                    if (c4 * 4 < p.ldc)
+                    if (c4 * 4 < p.wcols)
                         *reinterpret_cast<float4*>(em_r + c4 * 4) = make_float4(v[c4 * 4], v[c4 * 4 + 1], v[c4 * 4 + 2], v[c4 * 4 + 3]);
-                p.rowterm[row] = rt;
+                if (p.raw < 2) p.rowterm[row] = rt;
             }
             // per-video offset: the tile lies inside one video, one f64 atomic per warp
             contrib = warp_sum(contrib);
@@ -367,10 +377,51 @@ __global__ void emission_split_w_kernel(const float* __restrict__ w, int C, int 
     }
 }
 
+// Second half of the class-block passes (C > 64): every live row of em holds the unshifted scores of all C classes and
+// rowterm the class-independent term.  One warp per row: m = max_c (score + penalty), em = score - m (+ penalty),
+// rowterm += m, offset[b] += sum of rowterm -- what the single-launch epilogue does in registers.
+constexpr int FIN_ROWS = 64;  // rows of one video per CTA
+__global__ void __launch_bounds__(256) emission_finish_kernel(float* __restrict__ em, int ldc, int C, const float* __restrict__ penalty,
+                                                              const int32_t* __restrict__ lengths, int B, int Tmax,
+                                                              float* __restrict__ rowterm, double* __restrict__ offset) {
+    const int tpv = (Tmax + FIN_ROWS - 1) / FIN_ROWS;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long ntiles = (long long)B * tpv;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int b = (int)(tile / tpv);
+        const int t0 = (int)(tile - (long long)b * tpv) * FIN_ROWS;
+        const int len = min(max(lengths[b], 0), Tmax);
+        if (t0 >= len) continue;
+        double contrib = 0.0;
+        for (int t = t0 + warp; t < min(t0 + FIN_ROWS, len); t += 8) {
+            const long long row = (long long)b * Tmax + t;
+            float* em_r = em + (size_t)row * ldc;
+            const float* pen_r = penalty ? penalty + (size_t)row * C : nullptr;
+            float m = NEG;
+            for (int c = lane; c < C; c += 32) m = fmaxf(m, em_r[c] + (pen_r ? __ldg(pen_r + c) : 0.0f));
+            m = warp_max(m);
+            for (int c = lane; c < C; c += 32) {
+                float o = em_r[c] - m;
+                if (pen_r) o += __ldg(pen_r + c);
+                em_r[c] = o;
+            }
+            if (lane == 0) {
+                const float rt = rowterm[row] + m;
+                rowterm[row] = rt;
+                contrib += (double)rt;
+            }
+        }
+        if (lane == 0 && contrib != 0.0) atomicAdd(offset + b, contrib);
+    }
+}
+
 struct Plan {
     int npad, nchunk, nstage;
     size_t smem;
+    bool half;  // two CTAs per SM, 256 TMEM columns each
 };
+constexpr int CBLK = 64;      // classes per pass when C > 64
+constexpr int MAX_CBLK = 8;   // C <= 512
 
 static bool plan(int D, int C, Plan* pl) {
     if (C > 64 || D % 4 != 0 || D < 4) return false;
@@ -386,8 +437,21 @@ static bool plan(int D, int C, Plan* pl) {
     if (fixed + 2 * (size_t)STAGE_BYTES > cap) return false;
     int ns = (int)((cap - fixed) / STAGE_BYTES);
     if (ns > MAX_STAGES) ns = MAX_STAGES;
+    pl->half = false;
+    {
+        // two co-resident CTAs (each its own producer / converters / issuer / epilogue, 256 TMEM columns, 3-4 stages):
+        // one CTA's ring refill overlaps the other's, and the prologue of the next task's launch overlaps this one's tail
+        static const int two = [] { const char* e = getenv("HSMM_EMISSION_TWO_CTAS"); return e ? atoi(e) : 1; }();  // A/B switch, r02q: 934 -> 795 us
+        const size_t per_cta = (227 * 1024) / 2 - 1024;
+        if (two && pl->npad <= 32 && fixed + 3 * (size_t)STAGE_BYTES <= per_cta) {
+            ns = (int)((per_cta - fixed) / STAGE_BYTES);
+            if (ns > 4) ns = 4;
+            pl->half = true;
+        }
+    }
     pl->nstage = ns;
     pl->smem = fixed + (size_t)ns * STAGE_BYTES;
+    if (pl->half) return true;
     // the kernel allocates all 512 TMEM columns: never two of its CTAs on one SM (the second would sit in tcgen05.alloc)
     if (pl->smem < 117 * 1024) pl->smem = 117 * 1024;
     return true;
@@ -397,8 +461,13 @@ static bool plan(int D, int C, Plan* pl) {
 
 size_t emission_tc_workspace_bytes(int D, int C) {
     etc::Plan pl;
-    if (!etc::plan(D, C, &pl)) return 0;
-    return (size_t)2 * pl.npad * pl.nchunk * etc::KC * sizeof(float);
+    size_t total = 0;
+    if (C > etc::CBLK * etc::MAX_CBLK) return 0;
+    for (int c0 = 0; c0 < C; c0 += etc::CBLK) {  // one split weight table per class block
+        if (!etc::plan(D, C - c0 < etc::CBLK ? C - c0 : etc::CBLK, &pl)) return 0;
+        total += (size_t)2 * pl.npad * pl.nchunk * etc::KC * sizeof(float);
+    }
+    return total;
 }
 
 // returns 1 when the shape / alignment is not eligible (caller falls back to the SIMT kernel), 0 on launch, < 0 on error
@@ -406,52 +475,84 @@ int launch_emission_tc(const float* X, const float* w, const float* bias, const 
                        const float* penalty, const int32_t* lengths, int B, int Tmax, int D, int C, int ldc, float* em,
                        float* rowterm, double* offset, void* workspace, int num_sms, cudaStream_t st) {
     using namespace etc;
-    Plan pl;
-    if (!workspace || !plan(D, C, &pl)) return 1;
+    if (!workspace || C < 1 || C > CBLK * MAX_CBLK) return 1;
     if ((reinterpret_cast<uintptr_t>(X) & 15) || (reinterpret_cast<uintptr_t>(workspace) & 15) ||
-        (reinterpret_cast<uintptr_t>(em) & 15) || ldc % 4 != 0 || ldc > pl.npad)
+        (reinterpret_cast<uintptr_t>(em) & 15) || ldc % 4 != 0 || ldc < C)
         return 1;
     const long long rows = (long long)B * Tmax;
     if (rows >= (1ll << 31) - TILE_M) return 1;
-    const int dpad = pl.nchunk * KC;
-    CUtensorMap mx, mw;
+    // C <= 64: one launch scores, shifts and stores.  C > 64: one launch per block of 64 classes (X is re-read per block:
+    // 800 B a frame against the block's 64 x D multiply-adds the SIMT kernel would issue) + the finishing kernel
+    const int nblk = (C + CBLK - 1) / CBLK;
+    Plan pl[MAX_CBLK];
+    CUtensorMap mx, mw[MAX_CBLK];
+    float* wsp[MAX_CBLK];
+    {
+        float* wp = reinterpret_cast<float*>(workspace);
+        for (int k = 0; k < nblk; ++k) {
+            const int c0 = k * CBLK, cn = C - c0 < CBLK ? C - c0 : CBLK;
+            if (!plan(D, cn, &pl[k])) return 1;
+            const int wcols = (k + 1 < nblk) ? CBLK : ldc - c0;
+            if (wcols > pl[k].npad) return 1;
+            const int dpad = pl[k].nchunk * KC;
+            wsp[k] = wp;
+            if (!make_map(&mw[k], wp, (uint64_t)(2 * pl[k].npad), (uint64_t)dpad, (uint64_t)dpad, KC, (uint32_t)pl[k].npad)) return 1;
+            wp += (size_t)2 * pl[k].npad * dpad;
+        }
+    }
     if (!make_map(&mx, X, (uint64_t)rows, (uint64_t)D, (uint64_t)D, KC, TILE_M)) return 1;
-    if (!make_map(&mw, workspace, (uint64_t)(2 * pl.npad), (uint64_t)dpad, (uint64_t)dpad, KC, (uint32_t)pl.npad)) return 1;
 
     cudaError_t e = cudaMemsetAsync(offset, 0, sizeof(double) * B, st);
     if (e != cudaSuccess) {
         set_error("memset offset: %s", cudaGetErrorString(e));
         return -3;
     }
-    emission_split_w_kernel<<<(pl.npad * dpad + 255) / 256, 256, 0, st>>>(w, C, D, pl.npad, dpad, reinterpret_cast<float*>(workspace));
-    int rc = check_launch("emission_split_w_kernel");
-    if (rc) return rc;
-
-    Params p;
-    p.bias = bias; p.inv_var = inv_var; p.penalty = penalty; p.lengths = lengths; p.em = em; p.rowterm = rowterm;
-    p.offset = offset; p.row_const = row_const; p.B = B; p.Tmax = Tmax; p.D = D; p.C = C; p.ldc = ldc;
-    p.npad = pl.npad; p.nchunk = pl.nchunk; p.nstage = pl.nstage;
     const long long max_tiles = (long long)B * ((Tmax + TILE_M - 1) / TILE_M);
-    int grid = num_sms < max_tiles ? num_sms : (int)max_tiles;
-    if (grid < 1) grid = 1;
+    for (int k = 0; k < nblk; ++k) {
+        const long long want = pl[k].half ? 2ll * num_sms : num_sms;
+        int grid = want < max_tiles ? (int)want : (int)max_tiles;
+        if (grid < 1) grid = 1;
+        const int c0 = k * CBLK, cn = C - c0 < CBLK ? C - c0 : CBLK;
+        const int dpad = pl[k].nchunk * KC;
+        emission_split_w_kernel<<<(pl[k].npad * dpad + 255) / 256, 256, 0, st>>>(w + (size_t)c0 * D, cn, D, pl[k].npad, dpad, wsp[k]);
+        int rc = check_launch("emission_split_w_kernel");
+        if (rc) return rc;
 
-#define HSMM_ETC_LAUNCH(NB)                                                                                          \
-    {                                                                                                                \
-        e = cudaFuncSetAttribute(emission_tc_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem); \
-        if (e == cudaSuccess) emission_tc_kernel<NB><<<grid, THREADS, pl.smem, st>>>(mx, mw, p);                      \
+        Params p;
+        p.bias = bias + c0; p.inv_var = inv_var; p.penalty = penalty; p.lengths = lengths; p.em = em + c0; p.rowterm = rowterm;
+        p.offset = offset; p.row_const = row_const; p.B = B; p.Tmax = Tmax; p.D = D; p.C = cn; p.ldc = ldc;
+        p.raw = nblk == 1 ? 0 : (k == 0 ? 1 : 2);
+        p.wcols = nblk == 1 ? ldc : ((k + 1 < nblk) ? CBLK : ldc - c0);
+        p.npad = pl[k].npad; p.nchunk = pl[k].nchunk; p.nstage = pl[k].nstage;
+
+#define HSMM_ETC_LAUNCH(NB, H)                                                                                           \
+    {                                                                                                                   \
+        e = cudaFuncSetAttribute(emission_tc_kernel<NB, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl[k].smem); \
+        if (e == cudaSuccess) emission_tc_kernel<NB, H><<<grid, THREADS, pl[k].smem, st>>>(mx, mw[k], p);                    \
     }
-    switch (pl.npad / 16) {
-        case 1: HSMM_ETC_LAUNCH(1) break;
-        case 2: HSMM_ETC_LAUNCH(2) break;
-        case 3: HSMM_ETC_LAUNCH(3) break;
-        default: HSMM_ETC_LAUNCH(4) break;
-    }
+        switch (pl[k].npad / 16 + (pl[k].half ? 10 : 0)) {
+            case 1: HSMM_ETC_LAUNCH(1, false) break;
+            case 2: HSMM_ETC_LAUNCH(2, false) break;
+            case 3: HSMM_ETC_LAUNCH(3, false) break;
+            case 11: HSMM_ETC_LAUNCH(1, true) break;
+            case 12: HSMM_ETC_LAUNCH(2, true) break;
+            default: HSMM_ETC_LAUNCH(4, false) break;
+        }
 #undef HSMM_ETC_LAUNCH
-    if (e != cudaSuccess) {
-        set_error("emission_tc smem attr: %s", cudaGetErrorString(e));
-        return -3;
+        if (e != cudaSuccess) {
+            set_error("emission_tc smem attr: %s", cudaGetErrorString(e));
+            return -3;
+        }
+        rc = check_launch("emission_tc_kernel");
+        if (rc) return rc;
     }
-    return check_launch("emission_tc_kernel");
+    if (nblk > 1) {
+        long long ft = (long long)B * ((Tmax + FIN_ROWS - 1) / FIN_ROWS);
+        const int fgrid = (int)(ft < (long long)num_sms * 8 ? ft : (long long)num_sms * 8);
+        emission_finish_kernel<<<fgrid < 1 ? 1 : fgrid, 256, 0, st>>>(em, ldc, C, penalty, lengths, B, Tmax, rowterm, offset);
+        return check_launch("emission_finish_kernel");
+    }
+    return 0;
 }
 
 }  // namespace hsmm

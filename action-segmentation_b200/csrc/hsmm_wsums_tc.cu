@@ -47,9 +47,10 @@ constexpr size_t SMEM_BYTES = (size_t)NSTAGE * STAGE_BYTES + 128;
 
 struct Params {
     const int32_t* lengths;
-    float* out_wx;
-    float* out_wsum;
-    int B, Tmax, D, C;
+    float* out_wx;    // already offset to (first class, first feature) of this pass
+    float* out_wsum;  // offset to the first class of this pass; null for the passes over later feature blocks
+    int B, Tmax, D, C;  // D, C: feature dims / classes of THIS pass (<= 224, <= 32)
+    int ldo;            // row stride of out_wx = feature dims of the whole problem
     int nchunk;  // ceil(D / 32) <= 7
 };
 
@@ -256,8 +257,8 @@ weighted_sums_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
 #pragma unroll
                 for (int c = 0; c < NPAD; ++c) {
                     if (c < p.C) {
-                        if (d < p.D) atomicAdd(p.out_wx + (size_t)c * p.D + d, v[c]);
-                        if (d == 255) atomicAdd(p.out_wsum + c, v[c]);
+                        if (d < p.D) atomicAdd(p.out_wx + (size_t)c * p.ldo + d, v[c]);
+                        if (d == 255 && p.out_wsum) atomicAdd(p.out_wsum + c, v[c]);
                     }
                 }
             }
@@ -274,21 +275,21 @@ weighted_sums_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
 
 }  // namespace wtc
 
-// returns 1 when the shape / alignment is not eligible (caller falls back to the SIMT kernel), 0 on launch, < 0 on error
+// returns 1 when the shape / alignment is not eligible (caller falls back to the SIMT kernel), 0 on launch, < 0 on error.
+// One pass covers <= 224 feature dims x <= 32 classes (the TMEM accumulators); larger problems are tiled into passes over
+// feature blocks (X is read once in total) and class blocks (X is read once per class block): the README's D = 300
+// feature set (run_crosstask_i3d-resnet-audio.sh:13) takes 2 passes, Breakfast's C = 48 takes 2.  More than 3 class
+// blocks would re-read X more often than the SIMT kernel is slower: those shapes return 1.
 int launch_weighted_sums_tc(const float* X, const float* wgt, int ldc, const int32_t* lengths, int B, int Tmax, int D, int C,
                             float* out_wx, float* out_wsum, int num_sms, cudaStream_t st) {
     using namespace wtc;
-    if (D % 4 != 0 || D < 4 || D > 7 * KC || C < 1 || C > NPAD || ldc % 4 != 0 || ldc > NPAD) return 1;
+    constexpr int DBLK = 7 * KC, CBLK = NPAD;
+    if (D % 4 != 0 || D < 4 || C < 1 || ldc % 4 != 0 || ldc < C) return 1;
+    const int ncb = (C + CBLK - 1) / CBLK, ndb = (D + DBLK - 1) / DBLK;
+    if (ncb > 3 || ndb > 4) return 1;
     if ((reinterpret_cast<uintptr_t>(X) & 15) || (reinterpret_cast<uintptr_t>(wgt) & 15)) return 1;
     const long long rows = (long long)B * Tmax;
     if (rows < 1 || rows >= (1ll << 31) - TF) return 1;
-    CUtensorMap mx, mw;
-    if (!tc::make_map(&mx, X, (uint64_t)rows, (uint64_t)D, (uint64_t)D, KC, TF, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return 1;
-    if (!tc::make_map(&mw, wgt, (uint64_t)rows, (uint64_t)ldc, (uint64_t)ldc, KC, TF, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return 1;
-
-    Params p;
-    p.lengths = lengths; p.out_wx = out_wx; p.out_wsum = out_wsum; p.B = B; p.Tmax = Tmax; p.D = D; p.C = C;
-    p.nchunk = (D + KC - 1) / KC;
     const long long max_tiles = (long long)B * ((Tmax + TF - 1) / TF);
     int grid = num_sms < max_tiles ? num_sms : (int)max_tiles;
     if (grid < 1) grid = 1;
@@ -297,8 +298,30 @@ int launch_weighted_sums_tc(const float* X, const float* wgt, int ldc, const int
         set_error("weighted_sums_tc smem attr: %s", cudaGetErrorString(e));
         return -3;
     }
-    weighted_sums_tc_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(mx, mw, p);
-    return check_launch("weighted_sums_tc_kernel");
+    // every tensor map must encode before the first launch: a failure has to fall back to the SIMT kernel cleanly
+    CUtensorMap mx[4], mw[3];
+    for (int db = 0; db < ndb; ++db) {
+        const int d0 = db * DBLK, dn = (D - d0 < DBLK) ? D - d0 : DBLK;
+        if (!tc::make_map(&mx[db], X + d0, (uint64_t)rows, (uint64_t)dn, (uint64_t)D, KC, TF, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return 1;
+    }
+    for (int cb = 0; cb < ncb; ++cb) {
+        const int c0 = cb * CBLK, cn = (ldc - c0 < CBLK) ? ldc - c0 : CBLK;
+        if (!tc::make_map(&mw[cb], wgt + c0, (uint64_t)rows, (uint64_t)cn, (uint64_t)ldc, KC, TF, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return 1;
+    }
+    for (int cb = 0; cb < ncb; ++cb) {
+        const int c0 = cb * CBLK, cn = (C - c0 < CBLK) ? C - c0 : CBLK;
+        for (int db = 0; db < ndb; ++db) {
+            const int d0 = db * DBLK, dn = (D - d0 < DBLK) ? D - d0 : DBLK;
+            Params p;
+            p.lengths = lengths; p.out_wx = out_wx + (size_t)c0 * D + d0; p.out_wsum = db == 0 ? out_wsum + c0 : nullptr;
+            p.B = B; p.Tmax = Tmax; p.D = dn; p.C = cn; p.ldo = D;
+            p.nchunk = (dn + KC - 1) / KC;
+            weighted_sums_tc_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(mx[db], mw[cb], p);
+            const int rc = check_launch("weighted_sums_tc_kernel");
+            if (rc) return rc;
+        }
+    }
+    return 0;
 }
 
 }  // namespace hsmm

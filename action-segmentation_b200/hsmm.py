@@ -262,9 +262,11 @@ def feature_moments(features, lengths_i32):
     return sx, sx2
 
 
-def upload_ragged(host, dev, lengths_host_i32):
+def upload_ragged(host, dev, lengths_host_i32, lengths_dev_i32=None):
     """hsmm_upload_ragged: copy the live rows of a padded pinned host batch (B,T,width) into the device buffer `dev`
-    (same shape; its padding rows are left as they are) on the current stream.  Returns the bytes enqueued."""
+    (same shape; its padding rows are left as they are) on the current stream.  Returns the bytes enqueued.
+    With `lengths_dev_i32` (the lengths on the device) and a pinned `host` the copy is ONE kernel reading the host rows
+    over PCIe (hsmm_upload_ragged_mapped) instead of one copy-engine transfer per video."""
     lib = _lib.load()
     if host.is_cuda or not dev.is_cuda or host.dtype != torch.float32 or dev.dtype != torch.float32:
         raise _lib.HsmmError("upload_ragged: host must be a CPU float32 tensor and dev a CUDA float32 tensor")
@@ -272,6 +274,11 @@ def upload_ragged(host, dev, lengths_host_i32):
         raise _lib.HsmmError("upload_ragged: host and dev must be contiguous and of the same (B, T, width) shape")
     B, T, W = host.shape
     lh = lengths_host_i32.to(torch.int32).contiguous()
+    if lengths_dev_i32 is not None and host.is_pinned() and W % 4 == 0:
+        _need_cuda(lengths_dev_i32)
+        _lib.check(lib.hsmm_upload_ragged_mapped(ctypes.c_void_p(host.data_ptr()), _p(dev), _p(lengths_dev_i32), B, T, W, _stream()),
+                   "hsmm_upload_ragged_mapped")
+        return int(lh.clamp(0, T).sum()) * W * 4
     _lib.check(lib.hsmm_upload_ragged(ctypes.c_void_p(host.data_ptr()), _p(dev), ctypes.c_void_p(lh.data_ptr()), B, T, W,
                                       _stream()), "hsmm_upload_ragged")
     return int(lh.clamp(0, T).sum()) * W * 4

@@ -234,7 +234,7 @@ def packed_layout(tasks):
 
 
 def env_switches():
-    return {k: os.environ[k] for k in ("HSMM_BENCH_SKIP", "HSMM_BENCH_TASKS", "HSMM_BENCH_BUCKETS", "HSMM_BENCH_GROUPS", "HSMM_BENCH_FUSED", "HSMM_BENCH_NO_OVERLAP", "HSMM_BENCH_NO_REDUCE", "HSMM_DISABLE_LIN", "HSMM_DISABLE_PAIR", "HSMM_PAIR_MIN_VIDEOS",
+    return {k: os.environ[k] for k in ("HSMM_BENCH_SKIP", "HSMM_BENCH_TASKS", "HSMM_BENCH_BUCKETS", "HSMM_BENCH_GROUPS", "HSMM_BENCH_FUSED", "HSMM_BENCH_COPY_STREAMS", "HSMM_BENCH_UPLOAD", "HSMM_UPLOAD_CTAS", "HSMM_BENCH_PRIO", "HSMM_BENCH_VIT_LAST", "HSMM_BENCH_NO_OVERLAP", "HSMM_BENCH_NO_REDUCE", "HSMM_DISABLE_LIN", "HSMM_DISABLE_PAIR", "HSMM_PAIR_MIN_VIDEOS",
                                               "HSMM_FORCE_GENERIC") if os.environ.get(k)}
 
 
@@ -349,6 +349,14 @@ def device_step(tasks, streams, packed, layout, world, reduce=True, decode_only=
     return outs
 
 
+def make_streams(n_tasks):
+    """The step's streams: one per task (emission, weighted sums), then the DP streams of the task groups.
+    HSMM_BENCH_PRIO=1 (experiment) gives the streams behind the per-task ones a higher priority."""
+    n = min(2 * n_tasks, 36) + 1 + 18 * int(os.environ.get("HSMM_BENCH_BUCKETS", "0"))
+    prio = os.environ.get("HSMM_BENCH_PRIO", "0") == "1"
+    return [torch.cuda.Stream(priority=-1 if (prio and i >= n_tasks) else 0) for i in range(n)]
+
+
 def grouped_eligible(tasks):
     """hsmm_dp_grouped's envelope: sparse transition lists, K - 1 <= 20, C <= 32, one precision."""
     return all(tk.chain and tk.K - 1 <= 20 and tk.C <= 32 for tk in tasks) and len({tk.penalty is not None for tk in tasks}) == 1
@@ -393,10 +401,15 @@ def device_step_grouped(tasks, streams, packed, layout, world, reduce=True, n_gr
             s_x.wait_event(fork)
             for i in idx:
                 s_x.wait_event(em_ev[i])
-        with torch.cuda.stream(s_vit):
-            res = hsmm.grouped_dp(0, [dict(b, trans_list=tasks[i].pred, class_ids=tasks[i].class_ids) for b, i in zip(base, idx)])
-            for i, (spans, labels, _) in zip(idx, res):
-                outs[i] = (spans, labels, em_out[i][0], em_out[i][2])
+        def decode():
+            with torch.cuda.stream(s_vit):
+                res = hsmm.grouped_dp(0, [dict(b, trans_list=tasks[i].pred, class_ids=tasks[i].class_ids) for b, i in zip(base, idx)])
+                for i, (spans, labels, _) in zip(idx, res):
+                    outs[i] = (spans, labels, em_out[i][0], em_out[i][2])
+
+        vit_last = os.environ.get("HSMM_BENCH_VIT_LAST", "0") == "1"
+        if not vit_last:
+            decode()
         with torch.cuda.stream(s_dp):
             fb_in = []
             for b, i in zip(base, idx):
@@ -419,6 +432,8 @@ def device_step_grouped(tasks, streams, packed, layout, world, reduce=True, n_gr
                 bw = hsmm.grouped_dp(2, [dict(b, trans_list=b["trans_list2"], saved=f[1]) for b, f in zip(fb_in, fw)])
             bwd_done = torch.cuda.Event()
             bwd_done.record(s_dp)
+        if vit_last:
+            decode()
         for i, (logz, saved), (_, _, _, d_em) in zip(idx, fw, bw):
             tk = tasks[i]
             off, sizes = layout[i]
@@ -460,30 +475,38 @@ class HostBatch:
         self.h2d_bytes = live * tk.D * 4 + (0 if tk.penalty is None else live * tk.C * 4)
 
 
-def e2e_upload(tasks, host, copy_stream, slot):
-    """Host -> device copy of one step's inputs (live frames only) on the copy stream; returns the event to wait for."""
+def e2e_upload(tasks, host, copy_streams, slot):
+    """Host -> device copy of one step's inputs (live frames only); returns the events to wait for.  The tasks alternate
+    between the copy streams: a ragged upload is one ~1.6 MB copy per video, and back to back on ONE stream such copies
+    reach 46-50 GB/s of the 55 GB/s a single large copy gets on this box (~3.8 us of set-up each, r02q)."""
     from action_segmentation_b200 import hsmm
-    with torch.cuda.stream(copy_stream):
-        for tk, hb in zip(tasks, host):
-            hsmm.upload_ragged(hb.features, hb.dev_features[slot], hb.lengths_i32)
+    by_kernel = os.environ.get("HSMM_BENCH_UPLOAD", "kernel") == "kernel"  # hsmm_upload_ragged_mapped / hsmm_upload_ragged
+    for i, (tk, hb) in enumerate(zip(tasks, host)):
+        ld = tk.lengths_i32 if by_kernel else None
+        with torch.cuda.stream(copy_streams[i % len(copy_streams)]):
+            hsmm.upload_ragged(hb.features, hb.dev_features[slot], hb.lengths_i32, ld)
             if hb.penalty is not None:
-                hsmm.upload_ragged(hb.penalty, hb.dev_penalty[slot], hb.lengths_i32)
+                hsmm.upload_ragged(hb.penalty, hb.dev_penalty[slot], hb.lengths_i32, ld if tk.C % 4 == 0 else None)
+    evs = []
+    for cs in copy_streams:
         ev = torch.cuda.Event()
-        ev.record(copy_stream)
-    return ev
+        ev.record(cs)
+        evs.append(ev)
+    return evs
 
 
-def e2e_step(models, tasks, host, streams, copy_stream, slot, ready, decode_only=False):
+def e2e_step(models, tasks, host, streams, copy_streams, slot, ready, decode_only=False):
     """Public API with host buffers.  The inputs of THIS step (landing-buffer set `slot`) were uploaded while the previous
     step computed (`ready` = their event); this call first enqueues the upload of the NEXT step's inputs into the other
     set, then runs the module API on this step's and reads loss + predictions back.  Every step therefore contains one
     full host -> device copy of a step's inputs and the device -> host read of its results."""
-    nxt = e2e_upload(tasks, host, copy_stream, 1 - slot)
+    nxt = e2e_upload(tasks, host, copy_streams, 1 - slot)
     lls, preds = [], []
     ns = len(streams)
     for i, (m, tk, hb) in enumerate(zip(models, tasks, host)):
         st = streams[i % ns]
-        st.wait_event(ready)
+        for ev in ready:
+            st.wait_event(ev)
         with torch.cuda.stream(st):
             ends = None if tk.end is None else [[] for _ in range(tk.V)]
             feats, pen = hb.dev_features[slot], hb.dev_penalty[slot]
@@ -860,7 +883,7 @@ def run_train_decode(args, cfg, rank, world, device, barrier, sampler):
             return device_step_grouped(tasks, streams, packed, layout, world, reduce=reduce, n_groups=n_groups, fused=fused)
         return globals()["device_step"](tasks, streams, packed, layout, world, reduce=reduce)
 
-    streams = [torch.cuda.Stream() for _ in range(min(2 * len(tasks), 36) + 1 + 18 * int(os.environ.get("HSMM_BENCH_BUCKETS", "0")))]
+    streams = make_streams(len(tasks))
     D = cfg["D"]
 
     # ---- device-resident throughput -------------------------------------------------------------
@@ -1009,17 +1032,17 @@ def run_e2e(tasks, streams, frames_all, args, world, device, barrier, decode_onl
     host = [HostBatch(tk) for tk in tasks]
     h2d = sum(h.h2d_bytes for h in host)
     d2h = sum(tk.V * (tk.Tmax + 1) * 8 + tk.V * tk.Tmax * 8 + 4 for tk in tasks)
-    copy_stream = torch.cuda.Stream()
-    ready = e2e_upload(tasks, host, copy_stream, 0)  # prime the pipeline: inputs of the first (warm-up) step
+    copy_streams = [torch.cuda.Stream() for _ in range(int(os.environ.get("HSMM_BENCH_COPY_STREAMS", "3")))]
+    ready = e2e_upload(tasks, host, copy_streams, 0)  # prime the pipeline: inputs of the first (warm-up) step
     slot = 0
     for _ in range(max(1, min(args.warmup, 2))):
-        _, _, ready = e2e_step(models, tasks, host, streams, copy_stream, slot, ready, decode_only)
+        _, _, ready = e2e_step(models, tasks, host, streams, copy_streams, slot, ready, decode_only)
         slot = 1 - slot
     barrier()
     t0 = time.perf_counter()
     n_e2e = max(3, min(args.steps, 10))
     for _ in range(n_e2e):
-        _, _, ready = e2e_step(models, tasks, host, streams, copy_stream, slot, ready, decode_only)
+        _, _, ready = e2e_step(models, tasks, host, streams, copy_streams, slot, ready, decode_only)
         slot = 1 - slot
         if world > 1 and not decode_only:
             allreduce_all_gradients(models)

@@ -79,9 +79,10 @@ const char* hsmm_last_error(void);
  * synchronises to build it); penalty (B,Tmax,C) or NULL;
  * em (B,Tmax,ldc) out; rowterm (B,Tmax) out; offset (B) out (double, overwritten).
  * workspace: hsmm_emission_workspace_bytes(D, C) bytes (16-byte aligned) or NULL.  With a workspace and an
- * eligible shape (C <= 64, D % 4 == 0, X 16-byte aligned) the contraction runs on the tensor cores
- * (TMA-fed tcgen05.mma, operands split 3xTF32 so that the result is fp32-accurate); otherwise on a
- * SIMT fp32 kernel.  hsmm_emission_workspace_bytes returns 0 for shapes without a tensor-core plan.
+ * eligible shape (C <= 512, D % 4 == 0, X 16-byte aligned) the contraction runs on the tensor cores
+ * (TMA-fed tcgen05.mma, operands split 3xTF32 so that the result is fp32-accurate; C <= 64 in ONE launch that
+ * also shifts and stores, C > 64 in one launch per block of 64 classes followed by a row-shift kernel);
+ * otherwise on a SIMT fp32 kernel.  hsmm_emission_workspace_bytes returns 0 for shapes without a tensor-core plan.
  */
 size_t hsmm_emission_workspace_bytes(int D, int C);
 int hsmm_emission(const float* X, const float* w, const float* bias, const float* inv_var, const float* row_const,
@@ -177,9 +178,9 @@ int hsmm_dp_grouped(int mode, int n, const hsmm_dp_task* tasks, void* stream);
  *   out_wsum (C)  += sum_{b,t<len_b} weights[b,t,c]
  * weights (B,Tmax,ldc).  Both outputs are accumulated into (caller zeroes them).  Frames t >= lengths[b] are never
  * read into the sums, whatever they hold (NaN included), in X or in weights.
- * Eligible shapes (D <= 224, D % 4 == 0, C <= 32, ldc % 4 == 0, X and weights 16-byte aligned) run on the tensor cores
- * (TMA-fed tcgen05.mma over MN-major tf32 operands, 3xTF32 so that the sums are fp32-accurate); the others on a SIMT
- * fp32 kernel.
+ * Eligible shapes (D <= 896, D % 4 == 0, C <= 96, ldc % 4 == 0, X and weights 16-byte aligned) run on the tensor cores
+ * (TMA-fed tcgen05.mma over MN-major tf32 operands, 3xTF32 so that the sums are fp32-accurate; one launch per block of
+ * 224 features x 32 classes, so D <= 224 and C <= 32 is a single pass over X); the others on a SIMT fp32 kernel.
  */
 int hsmm_weighted_feature_sums(const float* X, const float* weights, int ldc, const int32_t* lengths,
                                int B, int Tmax, int D, int C, float* out_wx, float* out_wsum, void* stream);
@@ -214,6 +215,12 @@ int hsmm_feature_moments(const float* X, const int32_t* lengths, int B, int Tmax
  * `lengths_host` is a HOST array.  Asynchronous on `stream`.
  */
 int hsmm_upload_ragged(const float* host, float* dev, const int32_t* lengths_host, int B, int Tmax, int width, void* stream);
+/*
+ * The same copy done by a kernel: `host` must be pinned memory the device can address (cudaHostAlloc / torch
+ * pin_memory), `lengths` a DEVICE array, width % 4 == 0, both buffers 16-byte aligned.  One launch instead of one
+ * copy-engine transfer per video (each costs ~4 us of set-up: 45 instead of 55 GB/s at 1 MB per video).
+ */
+int hsmm_upload_ragged_mapped(const float* host, float* dev, const int32_t* lengths, int B, int Tmax, int width, void* stream);
 
 /* One-hot weights from labels: weights[b,t,c] = (labels[b,t] == c) for t < lengths[b] else 0. */
 int hsmm_onehot_weights(const int32_t* labels, const int32_t* lengths, int B, int Tmax, int C, int ldc,

@@ -37,7 +37,10 @@ def test_emission_golden(golden, case):
 
 @pytest.mark.parametrize("B,Tmax,D,C,pen", [(7, 300, 200, 23, False), (5, 257, 200, 13, True), (3, 700, 64, 48, False),
                                             (4, 130, 200, 7, True), (2, 1000, 300, 64, False), (3, 90, 36, 5, False),
-                                            (300, 40, 200, 23, False), (97, 300, 64, 9, True)])
+                                            (300, 40, 200, 23, False), (97, 300, 64, 9, True),
+                                            # C > 64: one launch per block of 64 classes + the finishing kernel
+                                            (5, 300, 200, 133, False), (4, 257, 64, 65, True), (3, 200, 200, 284, False),
+                                            (60, 70, 128, 130, True)])
 def test_emission_tensor_core_vs_oracle(B, Tmax, D, C, pen):
     """hsmm_emission on the tcgen05/TMA path (3xTF32) against the fp64 oracle (semimarkov_modules.py:324-381)
     and against the SIMT fp32 kernel: same em/rowterm/offset contract, fp32-level accuracy."""
@@ -300,10 +303,12 @@ def test_weighted_feature_sums_vs_numpy(B, Tmax, D, C):
 
 
 @pytest.mark.parametrize("B,Tmax,D,C", [(3, 100, 224, 32), (4, 130, 128, 16), (2, 64, 4, 1), (5, 257, 200, 23), (3, 90, 228, 9),
-                                        (2, 70, 200, 33), (300, 45, 200, 23), (130, 70, 204, 40)])
+                                        (2, 70, 200, 33), (300, 45, 200, 23), (130, 70, 204, 40), (40, 150, 300, 23), (9, 120, 300, 48),
+                                        (4, 200, 896, 96), (3, 64, 900, 12), (3, 64, 64, 97), (7, 100, 452, 65)])
 def test_weighted_feature_sums_tensor_core_edges(B, Tmax, D, C):
-    """The tcgen05 path of hsmm_weighted_feature_sums at the edges of its eligibility (D <= 224, C <= 32; the last two
-    shapes fall to the SIMT kernel), with a zero-length video, and with NaN in every padding frame of the features AND of
+    """The tcgen05 path of hsmm_weighted_feature_sums at the edges of its eligibility (one launch per block of 224 features x 32
+    classes, up to D = 896 and C = 96: the README's D = 300 features and Breakfast's 48 classes run here; D = 900 and C = 97
+    fall to the SIMT kernel), with a zero-length video, and with NaN in every padding frame of the features AND of
     the weights: frames t >= length must not reach the sums (the reference only ever sums the first length_b frames,
     semimarkov_utils.py:74-126)."""
     import action_segmentation_b200 as pkg
@@ -658,3 +663,31 @@ def test_em_statistics_and_closed_form_update():
     assert lls[-1] > lls[0] + 1.0, lls
     # the means moved towards the generating ones
     assert float((m.gaussian_means.detach() - true_means).norm()) < 0.5 * float((0.8 * torch.ones(C, D)).norm())
+
+
+@pytest.mark.parametrize("B,Tmax,W", [(5, 300, 200), (3, 77, 24), (40, 130, 64), (2, 9000, 200)])
+@pytest.mark.parametrize("mapped", [False, True])
+def test_upload_ragged_copies_exactly_the_live_rows(B, Tmax, W, mapped):
+    """hsmm_upload_ragged / hsmm_upload_ragged_mapped: the device buffer receives the rows t < lengths[b] of the padded
+    host batch (models/model.py:42-63 `padding_colate` + `.cuda()`), bit for bit, and keeps what it held behind them."""
+    import action_segmentation_b200 as pkg
+    rng = np.random.default_rng(B + Tmax + W)
+    lengths = rng.integers(0, Tmax + 1, size=B)
+    lengths[0] = Tmax
+    if B > 2:
+        lengths[1] = 0
+    host = torch.from_numpy(rng.normal(size=(B, Tmax, W)).astype(np.float32)).pin_memory()
+    dev = torch.full((B, Tmax, W), -7.0, device="cuda")
+    lh = torch.from_numpy(lengths).to(torch.int32)
+    n = pkg.hsmm.upload_ragged(host, dev, lh, lh.cuda() if mapped else None)
+    torch.cuda.synchronize()
+    assert n == int(lengths.sum()) * W * 4
+    got = dev.cpu()
+    for b, T in enumerate(lengths):
+        assert torch.equal(got[b, :T], host[b, :T])
+        assert (got[b, T:] == -7.0).all()
+    if mapped:  # pageable host memory is refused by the kernel path, not silently copied
+        lib = pkg._lib.load()
+        pageable = torch.zeros(B, Tmax, W)
+        rc = lib.hsmm_upload_ragged_mapped(pageable.data_ptr(), dev.data_ptr(), lh.cuda().data_ptr(), B, Tmax, W, None)
+        assert rc != 0
