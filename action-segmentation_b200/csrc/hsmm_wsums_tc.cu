@@ -31,19 +31,24 @@ namespace wtc {
 
 using namespace tc;
 
-constexpr int TF = 32;                       // frames per tile
 constexpr int KC = 32;                       // floats per 128-byte row
 constexpr int NCH = 8;                       // chunk slots per stage (256 feature columns)
-constexpr int CHUNK_BYTES = TF * 128;        // 4 KB: one chunk of one tile
-constexpr int XPART = NCH * CHUNK_BYTES;     // 32 KB
-constexpr int WPART = TF * 128;              // 4 KB
-constexpr int STAGE_BYTES = 2 * XPART + 2 * WPART;  // big + small of X and of the weights: 72 KB
 constexpr int NSTAGE = 3;
 constexpr int CONV_THREADS = 256;
 constexpr int THREADS = 64 + CONV_THREADS;
 constexpr int TMEM_COLS = 128;                // 2 feature halves x (NPAD columns x.wb + NPAD columns xb.ws)
 constexpr int NPAD = 32;                     // classes per accumulator (UMMA N)
-constexpr size_t SMEM_BYTES = (size_t)NSTAGE * STAGE_BYTES + 128;
+// TF = frames per tile (32: 72 KB stages, one CTA per SM)
+template <int TF>
+struct Geo {
+    static constexpr int CHUNK_BYTES = TF * 128;        // one chunk of one tile (4 KB at TF = 32)
+    static constexpr int XPART = NCH * CHUNK_BYTES;     // 32 KB
+    static constexpr int WPART = TF * 128;              // 4 KB
+    static constexpr int STAGE_BYTES = 2 * XPART + 2 * WPART;  // big + small of X and of the weights: 72 KB
+    static constexpr size_t SMEM_BYTES = (size_t)NSTAGE * STAGE_BYTES + 128;
+    static constexpr int XUNITS = (NCH - 1) * TF * 8;   // 16-byte units of the loadable chunk slots
+    static constexpr int XIT = (XUNITS + CONV_THREADS - 1) / CONV_THREADS;
+};
 
 struct Params {
     const int32_t* lengths;
@@ -55,8 +60,11 @@ struct Params {
 };
 
 // (THREADS, 2): <= 96 registers, 30 K per CTA: two DP CTAs stay resident beside this HBM-bound kernel
+template <int TF>
 __global__ void __launch_bounds__(THREADS, 2)
 weighted_sums_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w, const Params p) {
+    constexpr int CHUNK_BYTES = Geo<TF>::CHUNK_BYTES, XPART = Geo<TF>::XPART, WPART = Geo<TF>::WPART;
+    constexpr int STAGE_BYTES = Geo<TF>::STAGE_BYTES, XIT = Geo<TF>::XIT;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     if (smem_u32(smem_raw) & 1023u) __trap();
     uint8_t* st_s = smem_raw;
@@ -175,25 +183,28 @@ weighted_sums_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
             const int nf = min(TF, vlen - vj * TF);   // live frames of the tile
             uint8_t* sb = st_s + (size_t)st * STAGE_BYTES;
             mbar_wait(full + st, ph);
-            // X: 16-byte unit u of the stage <-> (chunk u >> 8, frame row (u >> 3) & 31); elementwise, in place
-            float4 x[NCH - 1];
+            // X: 16-byte unit u of the stage <-> (chunk u / (8 TF), frame row (u >> 3) % TF); elementwise, in place
+            const int xunits = p.nchunk * TF * 8;
+            float4 x[XIT];
 #pragma unroll
-            for (int i = 0; i < NCH - 1; ++i) {
+            for (int i = 0; i < XIT; ++i) {
                 const int u = tc_id + i * CONV_THREADS;
                 x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (i < p.nchunk) x[i] = *reinterpret_cast<const float4*>(sb + (size_t)u * 16);
+                if (u < xunits) x[i] = *reinterpret_cast<const float4*>(sb + (size_t)u * 16);
             }
             // weights: unit <-> (frame row tc_id >> 3, physical 16-byte slot tc_id & 7)
             const int wf = tc_id >> 3;
             const int wpj = tc_id & 7;                       // physical 16-byte slot; its 32-byte piece is permuted by (row & 3)
             const int wc0 = (((((wpj >> 1) ^ (wf & 3)) << 1) | (wpj & 1))) * 4;   // first class of the unit
-            float4 w = *reinterpret_cast<const float4*>(sb + 2 * XPART + (size_t)tc_id * 16);
-            const int xf = (tc_id >> 3) & 31;               // frame row of this thread's X units (the same for every chunk)
+            const bool wmine = tc_id < TF * 8;
+            float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (wmine) w = *reinterpret_cast<const float4*>(sb + 2 * XPART + (size_t)tc_id * 16);
+            const int xf = (tc_id >> 3) & (TF - 1);         // frame row of this thread's X units (the same for every i)
             const bool xlive = xf < nf;
 #pragma unroll
-            for (int i = 0; i < NCH - 1; ++i) {
-                if (i < p.nchunk) {
-                    const int u = tc_id + i * CONV_THREADS;
+            for (int i = 0; i < XIT; ++i) {
+                const int u = tc_id + i * CONV_THREADS;
+                if (u < xunits) {
                     float4 v = x[i];
                     if (!xlive) v = make_float4(0.f, 0.f, 0.f, 0.f);
                     float4 big, sml;
@@ -211,7 +222,7 @@ weighted_sums_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
                     *reinterpret_cast<float4*>(sb + XPART + (size_t)u * 16) = sml;
                 }
             }
-            {
+            if (wmine) {
                 if (wf >= nf) w = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (wc0 + 0 >= p.C) w.x = 0.f;
                 if (wc0 + 1 >= p.C) w.y = 0.f;
@@ -280,20 +291,18 @@ weighted_sums_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
 // feature blocks (X is read once in total) and class blocks (X is read once per class block): the README's D = 300
 // feature set (run_crosstask_i3d-resnet-audio.sh:13) takes 2 passes, Breakfast's C = 48 takes 2.  More than 3 class
 // blocks would re-read X more often than the SIMT kernel is slower: those shapes return 1.
-int launch_weighted_sums_tc(const float* X, const float* wgt, int ldc, const int32_t* lengths, int B, int Tmax, int D, int C,
-                            float* out_wx, float* out_wsum, int num_sms, cudaStream_t st) {
+template <int TF>
+static int launch_weighted_sums_tc_t(const float* X, const float* wgt, int ldc, const int32_t* lengths, int B, int Tmax, int D, int C,
+                                     float* out_wx, float* out_wsum, int ctas, cudaStream_t st) {
     using namespace wtc;
     constexpr int DBLK = 7 * KC, CBLK = NPAD;
-    if (D % 4 != 0 || D < 4 || C < 1 || ldc % 4 != 0 || ldc < C) return 1;
     const int ncb = (C + CBLK - 1) / CBLK, ndb = (D + DBLK - 1) / DBLK;
-    if (ncb > 3 || ndb > 4) return 1;
-    if ((reinterpret_cast<uintptr_t>(X) & 15) || (reinterpret_cast<uintptr_t>(wgt) & 15)) return 1;
     const long long rows = (long long)B * Tmax;
     if (rows < 1 || rows >= (1ll << 31) - TF) return 1;
     const long long max_tiles = (long long)B * ((Tmax + TF - 1) / TF);
-    int grid = num_sms < max_tiles ? num_sms : (int)max_tiles;
+    int grid = ctas < max_tiles ? ctas : (int)max_tiles;
     if (grid < 1) grid = 1;
-    cudaError_t e = cudaFuncSetAttribute(weighted_sums_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(weighted_sums_tc_kernel<TF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Geo<TF>::SMEM_BYTES);
     if (e != cudaSuccess) {
         set_error("weighted_sums_tc smem attr: %s", cudaGetErrorString(e));
         return -3;
@@ -316,12 +325,25 @@ int launch_weighted_sums_tc(const float* X, const float* wgt, int ldc, const int
             p.lengths = lengths; p.out_wx = out_wx + (size_t)c0 * D + d0; p.out_wsum = db == 0 ? out_wsum + c0 : nullptr;
             p.B = B; p.Tmax = Tmax; p.D = dn; p.C = cn; p.ldo = D;
             p.nchunk = (dn + KC - 1) / KC;
-            weighted_sums_tc_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(mx[db], mw[cb], p);
+            weighted_sums_tc_kernel<TF><<<grid, THREADS, Geo<TF>::SMEM_BYTES, st>>>(mx[db], mw[cb], p);
             const int rc = check_launch("weighted_sums_tc_kernel");
             if (rc) return rc;
         }
     }
     return 0;
+}
+
+int launch_weighted_sums_tc(const float* X, const float* wgt, int ldc, const int32_t* lengths, int B, int Tmax, int D, int C,
+                            float* out_wx, float* out_wsum, int num_sms, cudaStream_t st) {
+    using namespace wtc;
+    constexpr int DBLK = 7 * KC, CBLK = NPAD;
+    if (D % 4 != 0 || D < 4 || C < 1 || ldc % 4 != 0 || ldc < C) return 1;
+    if ((C + CBLK - 1) / CBLK > 3 || (D + DBLK - 1) / DBLK > 4) return 1;
+    if ((reinterpret_cast<uintptr_t>(X) & 15) || (reinterpret_cast<uintptr_t>(wgt) & 15)) return 1;
+    // tiles of 32 frames, one CTA per SM.  Tiles of 16 frames with two CTAs (two rings of three 36 KB stages) per SM were
+    // measured (r02q): same results, same time (configs[1] step 4.84 vs 4.82 ms) -- unlike the emission kernel this one
+    // is not bound by its ring
+    return launch_weighted_sums_tc_t<32>(X, wgt, ldc, lengths, B, Tmax, D, C, out_wx, out_wsum, num_sms, st);
 }
 
 }  // namespace hsmm

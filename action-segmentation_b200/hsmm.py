@@ -64,6 +64,9 @@ def prepare_lengths(lengths, device):
         lengths_dev = lengths.to(device=device, dtype=torch.int32).contiguous()
     else:
         lengths_dev = lengths.to(torch.int32).contiguous().pin_memory().to(device, non_blocking=True)
+    # longest first: with one video per warp the CTAs of short videos retire early and free their registers for the
+    # kernels queued behind (dealing every CTA one video of each length quantile was measured: the CTAs then all end
+    # together and the step is 8 % slower, r02q)
     order = torch.argsort(lengths_dev, descending=True, stable=True).to(torch.int32).contiguous()
     return lengths_dev, order
 
