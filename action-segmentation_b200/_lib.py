@@ -10,7 +10,7 @@ LIB_PATH = os.path.join(HERE, "libhsmm_b200.so")
 EXPORTS = [
     "hsmm_version", "hsmm_last_error", "hsmm_emission", "hsmm_emission_workspace_bytes", "hsmm_viterbi_workspace_bytes", "hsmm_logz_saved_bytes",
     "hsmm_viterbi", "hsmm_logz_forward", "hsmm_logz_backward", "hsmm_weighted_feature_sums", "hsmm_gold_score",
-    "hsmm_feature_moments", "hsmm_onehot_weights", "hsmm_dp_variant", "hsmm_launch_count", "hsmm_set_linear_window", "hsmm_set_generic_dp", "hsmm_upload_ragged", "hsmm_upload_ragged_mapped", "hsmm_dp_grouped", "hsmm_set_pair_min_videos",
+    "hsmm_feature_moments", "hsmm_onehot_weights", "hsmm_dp_variant", "hsmm_launch_count", "hsmm_set_linear_window", "hsmm_set_generic_dp", "hsmm_upload_ragged", "hsmm_upload_ragged_mapped", "hsmm_dp_grouped", "hsmm_set_pair_min_videos", "hsmm_set_mixed_min_videos",
 ]
 
 _lib = None
@@ -73,6 +73,8 @@ def load():
     lib.hsmm_dp_grouped.restype = i
     lib.hsmm_set_pair_min_videos.argtypes = [i]
     lib.hsmm_set_pair_min_videos.restype = i
+    lib.hsmm_set_mixed_min_videos.argtypes = [i]
+    lib.hsmm_set_mixed_min_videos.restype = i
     for name in ("hsmm_emission", "hsmm_viterbi", "hsmm_logz_forward", "hsmm_logz_backward", "hsmm_weighted_feature_sums",
                  "hsmm_gold_score", "hsmm_feature_moments", "hsmm_onehot_weights"):
         getattr(lib, name).restype = i
@@ -101,6 +103,11 @@ def set_generic_dp(force):
 def set_pair_min_videos(n):
     """Minimum number of videos in a call for the two-videos-per-warp kernels (hsmm_set_pair_min_videos)."""
     return int(load().hsmm_set_pair_min_videos(int(n)))
+
+
+def set_mixed_min_videos(n):
+    """Minimum number of videos of a grouped launch for the mixed-family kernels (hsmm_set_mixed_min_videos)."""
+    return int(load().hsmm_set_mixed_min_videos(int(n)))
 
 
 def set_linear_window(enabled):

@@ -43,6 +43,7 @@ static int num_sms() {
 bool dp_reg_supported(int C, int L, int mode, bool sparse, bool xp);
 bool dp_lin_used(int C, int L, int mode, bool sparse, bool xp);
 int dp_pair_set_min_videos(int n);
+int dp_mixed_set_min_videos(int n);
 int dp_lin_set_enabled(int on);
 const char* dp_reg_name(int C, int L, int mode, bool sparse, bool xp);
 int dp_reg_launch(DpParams p, int mode, cudaStream_t st);
@@ -172,6 +173,7 @@ int hsmm_set_generic_dp(int force) {
 
 int hsmm_set_linear_window(int enabled) { return dp_lin_set_enabled(enabled); }
 int hsmm_set_pair_min_videos(int n) { return dp_pair_set_min_videos(n); }
+int hsmm_set_mixed_min_videos(int n) { return dp_mixed_set_min_videos(n); }
 
 static size_t viterbi_base_bytes(int B, int Tmax, int C) {
     // [beta / back-pointer plane][predecessor plane][normaliser increments (B, Tmax+1)][flags (B)]

@@ -15,6 +15,7 @@ namespace hsmm {
 
 bool dp_lin_enabled();
 bool dp_pair_enabled_for(int videos);
+int dp_mixed_min_videos();
 
 // Forward and backward pass of a video back to back in ONE launch: a video's backward pass starts when ITS forward pass
 // ends instead of when the longest video of the launch has finished its forward pass, so the SMs stay full while the
@@ -35,6 +36,44 @@ __global__ void __launch_bounds__(128, 4) dp_pair_fb_kernel_grouped(const __grid
     dp_pair_forward_kernel_body<PAIR_KR>(g.t[t], local);
     __syncwarp();
     dp_pair_backward_kernel_body<PAIR_KR>(g.t[t], local);
+}
+
+// Both families in ONE launch (float state): tasks with C <= 16 run two videos per warp (VPB == 8 marks them), the others
+// one video per warp.  Two launches would run one after the other on the call's stream, each as long as its longest
+// video; one launch has a third fewer warps for the same videos (configs[1]: 1664 instead of 2304), so every scheduler
+// juggles ~3 instead of ~4 of these latency-bound instruction chains.
+__global__ void __launch_bounds__(128, 4) dp_mixed_fb_kernel_grouped(const __grid_constant__ DpGroup g) {
+    int local;
+    const int t = group_find(g, blockIdx.x, local);
+    if (g.t[t].VPB == 8) {
+        dp_pair_forward_kernel_body<PAIR_KR>(g.t[t], local);
+        __syncwarp();
+        dp_pair_backward_kernel_body<PAIR_KR>(g.t[t], local);
+    } else {
+        dp_lin_forward_kernel_body<false, 20, 1, 2>(g.t[t], local);
+        __syncwarp();
+        dp_lin_backward_kernel_body<false, 20, 1, 2>(g.t[t], local);
+    }
+}
+// (The same mix for Viterbi was measured, r02q: alone it is slower -- 1.96 instead of 1.63 ms for the 2304 videos of
+// configs[1], the two-videos-per-warp chain is longer per frame and a lone Viterbi launch is latency-bound -- and beside
+// the forward+backward launch it gains 1 %: Viterbi groups stay on one kernel family.)
+
+// per-task videos per block: 8 for the tasks in `pair8` (may be null), else 4
+static int fill_group_mixed(DpGroup& g, const DpParams* ps, int n, const bool* pair8) {
+    g.n = n;
+    int first = 0;
+    for (int i = 0; i < n; ++i) {
+        const int vpb = (pair8 && pair8[i]) ? 8 : 4;
+        g.t[i] = ps[i];
+        g.t[i].W = 1;
+        g.t[i].VPB = vpb;
+        g.t[i].only_flagged = 0;
+        g.first[i] = first;
+        first += (ps[i].B + vpb - 1) / vpb;
+    }
+    g.first[n] = first;
+    return first;
 }
 
 static int fill_group(DpGroup& g, const DpParams* ps, const int* idx, int n, int videos_per_block, int only_flagged) {
@@ -129,7 +168,24 @@ int dp_group_launch(const DpParams* ps, int n, int mode, cudaStream_t st) {
             large[nl++] = i;
     }
     int rc = 0;
-    if (lin) {
+    // mixed launch: float state, forward+backward, enough videos for the launch to be issue-bound, and at least one task
+    // that can run two videos per warp (otherwise the one-video kernel below is the same thing)
+    bool mixed = false;
+    const int mixed_min = dp_mixed_min_videos();
+    if (lin && !xp && !pair && mode == 3 && mixed_min >= 0 && videos >= mixed_min) {
+        bool p8[GROUP_MAX];
+        int n8 = 0;
+        for (int i = 0; i < n; ++i) n8 += (p8[i] = pair_shape_ok(ps[i].C, ps[i].L, true, false));
+        if (n8 > 0) {
+            const int blocks = fill_group_mixed(g, ps, n, p8);
+            const size_t sm_lin = 4 * (2 * 32 + 2) * sizeof(float);
+            dp_mixed_fb_kernel_grouped<<<blocks, 128, sm_lin, st>>>(g);
+            rc = check_launch("grouped mixed-family DP kernel");
+            if (rc) return rc;
+            mixed = true;
+        }
+    }
+    if (lin && !mixed) {
         if (ns) {
             const int blocks = fill_group(g, ps, small, ns, 8, 0);
             rc = launch_pair_group(g, blocks, mode, st);

@@ -56,6 +56,24 @@ int dp_pair_set_min_videos(int n) {
     g_pair_min.store(n < 0 ? -1 : n, std::memory_order_relaxed);
     return prev;
 }
+// Grouped launches (hsmm_dp_grouped): from this many videos on, the C <= 16 tasks of a float-state group run two videos per
+// warp INSIDE the same launch as the other tasks (hsmm_dp_group.cu: dp_mixed_*).  HSMM_MIXED_MIN_VIDEOS /
+// hsmm_set_mixed_min_videos() override it (0 = always, negative = never); never when the pair kernels are disabled.
+static std::atomic<int> g_mixed_min{-2};
+int dp_mixed_min_videos() {
+    int v = g_mixed_min.load(std::memory_order_relaxed);
+    if (v == -2) {
+        const char* e = getenv("HSMM_MIXED_MIN_VIDEOS");
+        v = e ? atoi(e) : 1024;
+        g_mixed_min.store(v < 0 ? -1 : v, std::memory_order_relaxed);
+    }
+    return pair_min_videos() < 0 ? -1 : v;
+}
+int dp_mixed_set_min_videos(int n) {
+    const int prev = dp_mixed_min_videos();
+    g_mixed_min.store(n < 0 ? -1 : n, std::memory_order_relaxed);
+    return prev;
+}
 bool dp_pair_enabled_for(int videos) {
     const int m = pair_min_videos();
     return m >= 0 && videos >= m;

@@ -606,40 +606,61 @@ def kernel_breakdown(tasks, reps=3, decode_only=False):
 
 
 def kernel_breakdown_grouped(tasks, reps=3, fused=True):
-    """As `kernel_breakdown` for the grouped step: emission and weighted sums per task, each DP pass as ONE grouped call."""
+    """As `kernel_breakdown` for the grouped step: emission and weighted sums per task, each DP pass as ONE grouped call.
+    Every family is captured into its own CUDA graph after an eager warm-up and the graph's replays are timed with CUDA
+    events on the launching stream: device time of the family's kernels, serialised, without the host time of the Python
+    calls between them (which a pair of events around the eager calls would include)."""
     from action_segmentation_b200 import hsmm
-    best = {}
-
-    def timed(key, fn):
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        r = fn()
-        b.record()
-        b.synchronize()
-        best[key] = min(best.get(key, 1e30), a.elapsed_time(b))
-        return r
-
     xp = tasks[0].penalty is not None
-    for rep in range(reps):
-        ems = [timed(("emission", i), lambda: hsmm.emission_scores(tk.X, tk.means, tk.cov_diag, tk.penalty, tk.lengths_i32,
-                                                                  params=tk.eparams)) for i, tk in enumerate(tasks)]
-        base = [dict(em=e[0], C=tk.C, init=tk.init, trans=tk.trans, lenp=tk.lenp, end=tk.end, offset=e[2], lengths_i32=tk.lengths_i32,
-                     order=tk.order, f64_state=xp) for tk, e in zip(tasks, ems)]
-        if fused:
-            fb = timed(("logz_forward_backward", 0), lambda: hsmm.grouped_dp(3, [dict(b, trans_list=tk.pred, trans_list2=tk.succ,
-                                                                                      grad=tk.gradw) for b, tk in zip(base, tasks)]))
-            fw, bw = None, [r[2:] for r in fb]
-        else:
-            fw = timed(("logz_forward", 0), lambda: hsmm.grouped_dp(1, [dict(b, trans_list=tk.pred) for b, tk in zip(base, tasks)]))
-            bw = timed(("logz_backward", 0), lambda: hsmm.grouped_dp(2, [dict(b, trans_list=tk.succ, saved=f[1], grad=tk.gradw)
-                                                                          for b, tk, f in zip(base, tasks, fw)]))
-        for i, (tk, r) in enumerate(zip(tasks, bw)):
-            timed(("weighted_feature_sums", i), lambda: hsmm.weighted_feature_sums(tk.X, r[3], tk.C, tk.lengths_i32))
-        timed(("viterbi", 0), lambda: hsmm.grouped_dp(0, [dict(b, trans_list=tk.pred, class_ids=tk.class_ids) for b, tk in zip(base, tasks)]))
-        del fw, bw
-    names = ["emission"] + (["logz_forward_backward"] if fused else ["logz_forward", "logz_backward"]) + ["weighted_feature_sums", "viterbi"]
-    kms = {n: sum(v for (k, _), v in best.items() if k == n) for n in names}
-    launches = {n: sum(1 for (k, _) in best if k == n) for n in names}
+    keep = {}
+
+    def f_emission():
+        keep["ems"] = [hsmm.emission_scores(tk.X, tk.means, tk.cov_diag, tk.penalty, tk.lengths_i32, params=tk.eparams) for tk in tasks]
+        keep["base"] = [dict(em=e[0], C=tk.C, init=tk.init, trans=tk.trans, lenp=tk.lenp, end=tk.end, offset=e[2],
+                             lengths_i32=tk.lengths_i32, order=tk.order, f64_state=xp) for tk, e in zip(tasks, keep["ems"])]
+
+    def f_fb():
+        fb = hsmm.grouped_dp(3, [dict(b, trans_list=tk.pred, trans_list2=tk.succ, grad=tk.gradw) for b, tk in zip(keep["base"], tasks)])
+        keep["bw"] = [r[2:] for r in fb]
+
+    def f_fwd():
+        keep["fw"] = hsmm.grouped_dp(1, [dict(b, trans_list=tk.pred) for b, tk in zip(keep["base"], tasks)])
+
+    def f_bwd():
+        keep["bw"] = hsmm.grouped_dp(2, [dict(b, trans_list=tk.succ, saved=f[1], grad=tk.gradw)
+                                         for b, tk, f in zip(keep["base"], tasks, keep["fw"])])
+
+    def f_wsums():
+        keep["ws"] = [hsmm.weighted_feature_sums(tk.X, r[3], tk.C, tk.lengths_i32) for tk, r in zip(tasks, keep["bw"])]
+
+    def f_vit():
+        keep["vit"] = hsmm.grouped_dp(0, [dict(b, trans_list=tk.pred, class_ids=tk.class_ids) for b, tk in zip(keep["base"], tasks)])
+
+    fams = [("emission", f_emission, len(tasks))]
+    fams += [("logz_forward_backward", f_fb, 1)] if fused else [("logz_forward", f_fwd, 1), ("logz_backward", f_bwd, 1)]
+    fams += [("weighted_feature_sums", f_wsums, len(tasks)), ("viterbi", f_vit, 1)]
+    kms, launches = {}, {}
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for name, fn, n in fams:
+            fn()  # eager warm-up (allocations, lazy module loads)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                fn()
+            best = 1e30
+            for _ in range(reps):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(side)
+                g.replay()
+                b.record(side)
+                b.synchronize()
+                best = min(best, a.elapsed_time(b))
+            kms[name], launches[name] = best, n
+            keep["graph_" + name] = g  # the later families read this one's outputs: keep its pool alive
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
     return kms, launches
 
 
@@ -994,8 +1015,9 @@ def run_train_decode(args, cfg, rank, world, device, barrier, sampler):
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_frame": bpf,
                 "kernel_ms": {k: round(v, 3) for k, v in kms.items()}, "launches_per_step": klaunch,
-                "kernel_ms_note": "calls timed alone and serialised (API calls: a grouped DP call = its two or three kernels over all "
-                                  "tasks); in the step they overlap across streams",
+                "kernel_ms_note": "each family timed alone: its API calls captured into one CUDA graph, replays timed with CUDA events "
+                                  "on the launching stream (a grouped DP call = its two or three kernels over all tasks; the "
+                                  "per-task calls of a family run one after the other); in the step they overlap across streams",
                 # whole step against the same peak, per GPU (step_bytes counts this rank's frames)
                 "step_achieved_gbs": step_bytes / (ms_per_step * 1e-3) / 1e9, "step_frac": step_frac,
                 "compute_ceiling": comp, "binding": "fp32_issue" if comp["frac"] > step_frac else "hbm"}

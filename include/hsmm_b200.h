@@ -256,6 +256,13 @@ int hsmm_set_linear_window(int enabled);
  * previous value. */
 int hsmm_set_pair_min_videos(int n);
 
+/* hsmm_dp_grouped, float state, forward+backward (mode 3): a group below the threshold above but with at least this many
+ * videos runs its C <= 16 tasks two videos per warp and its other tasks one video per warp in ONE launch (a third fewer
+ * warps for the same videos; two launches would run one after the other).  Default 1024 (environment:
+ * HSMM_MIXED_MIN_VIDEOS); 0 = always, negative = never; never when hsmm_set_pair_min_videos is negative.  Results do not
+ * depend on it.  Returns the previous value. */
+int hsmm_set_mixed_min_videos(int n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -23,10 +23,14 @@ def golden():
     return load
 
 
-@pytest.fixture(params=["one_video_per_warp", "two_videos_per_warp"])
+@pytest.fixture(params=["one_video_per_warp", "two_videos_per_warp", "mixed_in_one_launch"])
 def pair_mode(request):
-    """Run a test on both fast paths of the C <= 16 chain-constrained shapes (hsmm_set_pair_min_videos)."""
+    """Run a test on the fast paths of the C <= 16 chain-constrained shapes (hsmm_set_pair_min_videos): one video per warp,
+    two videos per warp, and -- for grouped launches -- both families inside one launch (hsmm_set_mixed_min_videos)."""
     import action_segmentation_b200 as pkg
-    prev = pkg._lib.set_pair_min_videos(0 if request.param == "two_videos_per_warp" else -1)
+    mixed = request.param == "mixed_in_one_launch"
+    prev_m = pkg._lib.set_mixed_min_videos(0 if mixed else -1)   # read before the pair switch: "never pair" hides it
+    prev = pkg._lib.set_pair_min_videos({"one_video_per_warp": -1, "two_videos_per_warp": 0}.get(request.param, 1 << 30))
     yield request.param
     pkg._lib.set_pair_min_videos(prev)
+    pkg._lib.set_mixed_min_videos(prev_m)
