@@ -58,10 +58,10 @@ struct Params {
     int nstage;   // ring depth
 };
 
-template <int NB, bool HALF>  // NPAD = 16 * NB; HALF: 256 TMEM columns (NB <= 2, at most 4 stages), so that two CTAs share an SM
-// (THREADS, 2): caps the kernel at 96 registers -- 30 K registers per CTA, so that two CTAs of the DP kernels (12-16 K
+template <int NB, bool HALF, int MINB>  // NPAD = 16 * NB; HALF: 256 TMEM columns (NB <= 2, at most 4 stages), so that two CTAs share an SM
+// MINB = 2 caps the kernel at 96 registers -- 30 K registers per CTA, so that two CTAs of the DP kernels (12-16 K
 // registers each) stay resident beside it and use the issue slots this HBM-bound kernel leaves idle
-__global__ void __launch_bounds__(THREADS, 2)
+__global__ void __launch_bounds__(THREADS, MINB)
 emission_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w, const Params p) {
     constexpr int NPAD = 16 * NB;
     // One accumulator = 2 NPAD TMEM columns: [0, NPAD) collects xb.wb + xs.wb, [NPAD, 2 NPAD) collects xb.ws (the big and
@@ -525,18 +525,21 @@ int launch_emission_tc(const float* X, const float* w, const float* bias, const 
         p.wcols = nblk == 1 ? ldc : ((k + 1 < nblk) ? CBLK : ldc - c0);
         p.npad = pl[k].npad; p.nchunk = pl[k].nchunk; p.nstage = pl[k].nstage;
 
-#define HSMM_ETC_LAUNCH(NB, H)                                                                                           \
+#define HSMM_ETC_LAUNCH(NB, H, M)                                                                                           \
     {                                                                                                                   \
-        e = cudaFuncSetAttribute(emission_tc_kernel<NB, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl[k].smem); \
-        if (e == cudaSuccess) emission_tc_kernel<NB, H><<<grid, THREADS, pl[k].smem, st>>>(mx, mw[k], p);                    \
+        e = cudaFuncSetAttribute(emission_tc_kernel<NB, H, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl[k].smem); \
+        if (e == cudaSuccess) emission_tc_kernel<NB, H, M><<<grid, THREADS, pl[k].smem, st>>>(mx, mw[k], p);                    \
     }
+        // min-blocks 2 (<= 96 registers) up to 32 classes: two of these CTAs, or one beside two DP CTAs, share an SM.  Above,
+        // shared memory allows one CTA per SM anyway and the epilogue's 4 NB + 16 accumulator registers per row spill under
+        // that cap (r02s, graph-timed, 1.8 M frames: C = 48 2.33 -> 2.76 TB/s, C = 64 1.27 -> 2.22 TB/s without it)
         switch (pl[k].npad / 16 + (pl[k].half ? 10 : 0)) {
-            case 1: HSMM_ETC_LAUNCH(1, false) break;
-            case 2: HSMM_ETC_LAUNCH(2, false) break;
-            case 3: HSMM_ETC_LAUNCH(3, false) break;
-            case 11: HSMM_ETC_LAUNCH(1, true) break;
-            case 12: HSMM_ETC_LAUNCH(2, true) break;
-            default: HSMM_ETC_LAUNCH(4, false) break;
+            case 1: HSMM_ETC_LAUNCH(1, false, 2) break;
+            case 2: HSMM_ETC_LAUNCH(2, false, 2) break;
+            case 3: HSMM_ETC_LAUNCH(3, false, 1) break;
+            case 11: HSMM_ETC_LAUNCH(1, true, 2) break;
+            case 12: HSMM_ETC_LAUNCH(2, true, 2) break;
+            default: HSMM_ETC_LAUNCH(4, false, 1) break;
         }
 #undef HSMM_ETC_LAUNCH
         if (e != cudaSuccess) {
