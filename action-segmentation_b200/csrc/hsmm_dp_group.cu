@@ -42,7 +42,8 @@ __global__ void __launch_bounds__(128, 4) dp_pair_fb_kernel_grouped(const __grid
 // one video per warp.  Two launches would run one after the other on the call's stream, each as long as its longest
 // video; one launch has a third fewer warps for the same videos (configs[1]: 1664 instead of 2304), so every scheduler
 // juggles ~3 instead of ~4 of these latency-bound instruction chains.
-__global__ void __launch_bounds__(128, 4) dp_mixed_fb_kernel_grouped(const __grid_constant__ DpGroup g) {
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) dp_mixed_fb_kernel_grouped(const __grid_constant__ DpGroup g) {
     int local;
     const int t = group_find(g, blockIdx.x, local);
     if (g.t[t].VPB == 8) {
@@ -110,6 +111,8 @@ static int launch_lin_group(DpGroup& g, int blocks, int mode, cudaStream_t st) {
         // 4 CTAs per SM for the float-state pair (128 registers); forcing 5 spills the windows and doubles the time (r02p A/B)
         if constexpr (XP)
             dp_lin_fb_kernel_grouped<XP, 1><<<blocks, 128, smem, st>>>(g);
+        else if (blocks <= 3 * dp_num_sms())
+            dp_lin_fb_kernel_grouped<false, 3><<<blocks, 128, smem, st>>>(g);
         else
             dp_lin_fb_kernel_grouped<false, 4><<<blocks, 128, smem, st>>>(g);
     } else if (mode == 0)
@@ -179,7 +182,12 @@ int dp_group_launch(const DpParams* ps, int n, int mode, cudaStream_t st) {
         if (n8 > 0) {
             const int blocks = fill_group_mixed(g, ps, n, p8);
             const size_t sm_lin = 4 * (2 * 32 + 2) * sizeof(float);
-            dp_mixed_fb_kernel_grouped<<<blocks, 128, sm_lin, st>>>(g);
+            // up to 3 x SMs CTAs: compiled for three CTAs per SM (152 instead of 128 registers: the backward loops lose a
+            // tenth of their instructions; r02u: the call 2.52 -> 2.15 ms, the configs[1] step 4.52 -> 4.20 ms)
+            if (blocks <= 3 * dp_num_sms())
+                dp_mixed_fb_kernel_grouped<3><<<blocks, 128, sm_lin, st>>>(g);
+            else
+                dp_mixed_fb_kernel_grouped<4><<<blocks, 128, sm_lin, st>>>(g);
             rc = check_launch("grouped mixed-family DP kernel");
             if (rc) return rc;
             mixed = true;

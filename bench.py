@@ -234,7 +234,7 @@ def packed_layout(tasks):
 
 
 def env_switches():
-    return {k: os.environ[k] for k in ("HSMM_BENCH_SKIP", "HSMM_BENCH_TASKS", "HSMM_BENCH_BUCKETS", "HSMM_BENCH_GROUPS", "HSMM_BENCH_FUSED", "HSMM_BENCH_COPY_STREAMS", "HSMM_BENCH_UPLOAD", "HSMM_UPLOAD_CTAS", "HSMM_BENCH_PRIO", "HSMM_BENCH_VIT_LAST", "HSMM_BENCH_NO_OVERLAP", "HSMM_BENCH_NO_REDUCE", "HSMM_DISABLE_LIN", "HSMM_DISABLE_PAIR", "HSMM_PAIR_MIN_VIDEOS",
+    return {k: os.environ[k] for k in ("HSMM_BENCH_SKIP", "HSMM_BENCH_TASKS", "HSMM_BENCH_BUCKETS", "HSMM_BENCH_GROUPS", "HSMM_BENCH_FUSED", "HSMM_BENCH_ORDERED_GROUPS", "HSMM_EMISSION_TWO_CTAS", "HSMM_BENCH_COPY_STREAMS", "HSMM_BENCH_UPLOAD", "HSMM_UPLOAD_CTAS", "HSMM_BENCH_PRIO", "HSMM_BENCH_VIT_LAST", "HSMM_BENCH_NO_OVERLAP", "HSMM_BENCH_NO_REDUCE", "HSMM_DISABLE_LIN", "HSMM_DISABLE_PAIR", "HSMM_PAIR_MIN_VIDEOS",
                                               "HSMM_FORCE_GENERIC") if os.environ.get(k)}
 
 
@@ -375,15 +375,24 @@ def device_step_grouped(tasks, streams, packed, layout, world, reduce=True, n_gr
     fork.record(cur)
     n, ns = len(tasks), len(streams)
     assert ns >= n + 2 * n_groups
-    em_out, em_ev = [], []
-    for i, tk in enumerate(tasks):
-        st = streams[i]
-        st.wait_event(fork)
-        with torch.cuda.stream(st):
-            em_out.append(hsmm.emission_scores(tk.X, tk.means, tk.cov_diag, tk.penalty, tk.lengths_i32, params=tk.eparams))
-            ev = torch.cuda.Event()
-            ev.record(st)
-            em_ev.append(ev)
+    em_out, em_ev = [None] * n, [None] * n
+    # HSMM_BENCH_ORDERED_GROUPS=1 (experiment): the emission launches of group g+1 wait for those of group g, so that they
+    # run under group g's DP instead of beside group g's emission
+    ordered = os.environ.get("HSMM_BENCH_ORDERED_GROUPS", "0") == "1" and n_groups > 1
+    prev_evs = []
+    for gi in range(n_groups if ordered else 1):
+        mine = list(range(gi, n, n_groups)) if ordered else list(range(n))
+        for i in mine:
+            tk, st = tasks[i], streams[i]
+            st.wait_event(fork)
+            for ev in prev_evs:
+                st.wait_event(ev)
+            with torch.cuda.stream(st):
+                em_out[i] = hsmm.emission_scores(tk.X, tk.means, tk.cov_diag, tk.penalty, tk.lengths_i32, params=tk.eparams)
+                ev = torch.cuda.Event()
+                ev.record(st)
+                em_ev[i] = ev
+        prev_evs = [em_ev[i] for i in mine]
     xp = tasks[0].penalty is not None
     outs = [None] * n
     used = list(streams[:n])
