@@ -570,6 +570,10 @@ def allreduce_all_gradients(models):
     for g in grads:
         g.copy_(flat[off:off + g.numel()].view_as(g))
         off += g.numel()
+    # The gradients were allocated on the per-task streams and are written here on the current one: the next step frees
+    # them (zero_grad) on ITS stream, whose allocator may hand the block out again at once -- e.g. to an index tensor --
+    # while these copies are still queued.  The reduced gradients are what the optimiser step consumes next anyway: wait.
+    torch.cuda.current_stream().synchronize()
 
 
 # ---------------------------------------------------------------------------------------------
@@ -1184,6 +1188,8 @@ def main():
     torch.cuda.set_device(local)
     device = "cuda:%d" % local
     if world > 1:
+        # stdout carries ONE JSON line: NCCL's own log (its version banner under NCCL_DEBUG=VERSION/WARN) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         torch.distributed.init_process_group("nccl", device_id=torch.device(device))
     import action_segmentation_b200  # noqa: F401
 
