@@ -1164,18 +1164,33 @@ def run_sweep(args, cfg, rank, world, device, barrier, sampler):
     }
 
 
+def emit(result):
+    """The ONE JSON line, on the process's original stdout."""
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT, (json.dumps(result) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
 def main():
+    global _REAL_STDOUT
     args = parse()
     cfg = config_of(args)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries ONE JSON line: whatever the libraries print meanwhile (NCCL's version banner, warnings of the
+    # reference's modules) goes to stderr -- file descriptor 1 points there until the line is written
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
 
     if args.impl == "reference":
         if rank != 0:
             return
         cb, dt = run_cpu_baseline(args, cfg, max(1, args.steps), max(0, min(args.warmup, 1)))
-        print(json.dumps({
+        emit(({
             "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": {"workload": workload_name(args, cfg), "sample": cb["sample"]},
@@ -1188,8 +1203,6 @@ def main():
     torch.cuda.set_device(local)
     device = "cuda:%d" % local
     if world > 1:
-        # stdout carries ONE JSON line: NCCL's own log (its version banner under NCCL_DEBUG=VERSION/WARN) goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         torch.distributed.init_process_group("nccl", device_id=torch.device(device))
     import action_segmentation_b200  # noqa: F401
 
@@ -1214,7 +1227,7 @@ def main():
             result["config"]["env_switches"] = sw
             if "HSMM_BENCH_SKIP" in sw or "HSMM_BENCH_TASKS" in sw or "HSMM_BENCH_NO_REDUCE" in sw:
                 result["invalid"] = "ablation run: HSMM_BENCH_SKIP / HSMM_BENCH_TASKS drop work from the timed region"
-        print(json.dumps(result))
+        emit(result)
     if world > 1:
         torch.distributed.destroy_process_group()
 
