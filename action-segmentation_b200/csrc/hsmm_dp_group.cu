@@ -110,7 +110,7 @@ static int launch_lin_group(DpGroup& g, int blocks, int mode, cudaStream_t st) {
     if (mode == 3) {
         // 4 CTAs per SM for the float-state pair (128 registers); forcing 5 spills the windows and doubles the time (r02p A/B)
         if constexpr (XP)
-            dp_lin_fb_kernel_grouped<XP, 1><<<blocks, 128, smem, st>>>(g);
+            dp_lin_fb_kernel_grouped<XP, 3><<<blocks, 128, smem, st>>>(g);
         else if (blocks <= 3 * dp_num_sms())
             dp_lin_fb_kernel_grouped<false, 3><<<blocks, 128, smem, st>>>(g);
         else

@@ -574,7 +574,8 @@ __device__ __forceinline__ void dp_lin_backward_kernel_body(const DpParams& p, c
 }
 
 template <bool XP, int KR, int S, int TM>
-__global__ void __launch_bounds__(128, (TM == 2 && KR <= 20 && !XP) ? 4 : 1) dp_lin_backward_kernel(const DpParams p) {
+// f64 state: 173 registers unbounded = two CTAs per SM; bounded to three it compiles to 162 without spills
+__global__ void __launch_bounds__(128, (TM == 2 && KR <= 20) ? (XP ? 3 : 4) : 1) dp_lin_backward_kernel(const DpParams p) {
     dp_lin_backward_kernel_body<XP, KR, S, TM>(p, blockIdx.x);
 }
 // the same body compiled for three CTAs per SM (<= 168 registers instead of 128: ~10 % fewer instructions per frame, no
@@ -584,7 +585,7 @@ __global__ void __launch_bounds__(128, 3) dp_lin_backward_kernel_wide(const DpPa
     dp_lin_backward_kernel_body<XP, KR, S, TM>(p, blockIdx.x);
 }
 template <bool XP, int KR, int S, int TM>
-__global__ void __launch_bounds__(128, (TM == 2 && KR <= 20 && !XP) ? 4 : 1) dp_lin_backward_kernel_grouped(const __grid_constant__ DpGroup g) {
+__global__ void __launch_bounds__(128, (TM == 2 && KR <= 20) ? (XP ? 3 : 4) : 1) dp_lin_backward_kernel_grouped(const __grid_constant__ DpGroup g) {
     int local;
     const int t = group_find(g, blockIdx.x, local);
     dp_lin_backward_kernel_body<XP, KR, S, TM>(g.t[t], local);

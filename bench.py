@@ -907,10 +907,11 @@ def run_train_decode(args, cfg, rank, world, device, barrier, sampler):
     frames = sum(tk.frames for tk in tasks)
     layout, total = packed_layout(tasks)
     packed = torch.zeros(total, device=device)
-    # forward + backward in one launch for the float-state kernels (the f64-state pair needs 172 registers: two launches,
-    # two half-groups so that one group's streaming kernels overlap the other's DP)
+    # forward + backward in one launch for the float-state kernels; the f64-state pair (162 registers: three CTAs per SM, not
+    # all 576 CTAs resident) runs as two launches over three task groups (r02u: unfused 3 / 2 / 1 groups 6.25 / 6.35 / 6.65 ms,
+    # fused 1 / 2 groups 6.74 / 6.67 ms)
     fused = os.environ.get("HSMM_BENCH_FUSED", "0" if cfg["narration"] else "1") == "1"
-    n_groups = int(os.environ.get("HSMM_BENCH_GROUPS", "1" if fused else "2"))
+    n_groups = int(os.environ.get("HSMM_BENCH_GROUPS", "1" if fused else "3"))
     grouped = n_groups > 0 and grouped_eligible(tasks) and len(tasks) > 1 and not os.environ.get("HSMM_BENCH_SKIP")
 
     def device_step(tasks, streams, packed, layout, world, reduce=True):  # noqa: F811 (the step of this run)

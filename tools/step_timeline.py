@@ -39,7 +39,7 @@ def main():
     layout, total = bench.packed_layout(tasks)
     packed = torch.zeros(total, device=device)
     fused = os.environ.get("HSMM_BENCH_FUSED", "0" if cfg["narration"] else "1") == "1"
-    n_groups = int(os.environ.get("HSMM_BENCH_GROUPS", "1" if fused else "2"))
+    n_groups = int(os.environ.get("HSMM_BENCH_GROUPS", "1" if fused else "3"))
     streams = bench.make_streams(len(tasks))
 
     def step():
