@@ -108,6 +108,12 @@ __device__ __forceinline__ void dp_lin_forward_kernel_body(const DpParams& p, co
     }
     // the window must stay inside float range: P <= 2^(max(maxstep,0) - len), len >= 2^-100
     bool bad = valid && (lnmin < -100.0f || fmaxf(maxstep, 0.0f) - lnmin > 110.0f);
+    if (__any_sync(FULL, bad)) {
+        // a length table this path cannot hold (e.g. Poisson tails at K = 100) is known before the first frame: hand the
+        // video to the log-domain kernel at once instead of after a full, discarded pass
+        if (lane == 0) p.fflag[b] = 2.0f;
+        return;
+    }
     const float ln_first = valid ? p.lenp[(size_t)C + c] * SC : NEG;  // len[1, c]
     const float init_c = valid ? p.init[c] * SC : NEG;
     const float* endb = p.end ? p.end + (size_t)b * C : nullptr;
@@ -595,7 +601,7 @@ __global__ void __launch_bounds__(128, (TM == 2 && KR <= 20) ? (XP ? 3 : 4) : 1)
 // host side: which shapes take the linear-window path
 // ---------------------------------------------------------------------------------------------
 // variants of kVariants that have a linear-window instantiation (one warp per video, lengths in registers)
-static inline bool lin_variant(int v) { return v == 0 || v == 1 || v == 2 || v == 3 || v == 6; }
+static inline bool lin_variant(int v) { return v == 0 || v == 1 || v == 2 || v == 3 || v == 6 || v == 10; }
 
 static inline bool lin_eligible(const RegChoice& ch, bool xp) {
     // extended-precision state (narration penalties): sparse transition lists only, the two CrossTask variants
@@ -640,6 +646,7 @@ static int launch_lin(const DpParams& p, const RegChoice& ch, cudaStream_t st) {
         case 2: return launch_lin_tm<MODE, 13, 4>(p, ch.tm, st);
         case 3: return launch_lin_tm<MODE, 25, 2>(p, ch.tm, st);
         case 6: return launch_lin_tm<MODE, 32, 1>(p, ch.tm, st);
+        case 10: return launch_lin_tm<MODE, 50, 2>(p, ch.tm, st);
     }
     set_error("no linear-window DP variant for this shape");
     return -2;

@@ -83,6 +83,10 @@ __device__ __forceinline__ void dp_pair_forward_kernel_body(const DpParams& p, c
         if (maxstep < -1.0e29f) maxstep = 0.0f;
     }
     bool bad = valid && (lnmin < -100.0f || fmaxf(maxstep, 0.0f) - lnmin > 110.0f);
+    if (__any_sync(FULL, bad)) {  // unsuitable length table (one task: both videos): known before the first frame
+        if (c == 0 && q.have) p.fflag[b] = 2.0f;
+        return;
+    }
     const float ln_first = valid ? p.lenp[(size_t)C + c] * SC : NEG;
     const float init_c = valid ? p.init[c] * SC : NEG;
     const float endc = valid ? (p.end ? p.end[(size_t)b * C + c] : 0.0f) * SC : NEG;

@@ -908,6 +908,7 @@ struct RegVariant {
 static const RegVariant kVariants[] = {
     {10, 2, true}, {20, 1, true}, {13, 4, true}, {25, 2, true}, {25, 4, true}, {25, 8, true}, {32, 1, true},
     {50, 4, false}, {50, 8, false}, {63, 8, false},
+    {50, 2, true},  // C <= 16 with windows of 51..100 frames in ONE warp (the S6 shape: C = 11, K = 100)
 };
 constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 constexpr int kMaxThreadsSmall1 = 128, kMaxThreadsSmall = 512;
@@ -944,6 +945,7 @@ static RegChoice choose(int C, int L, int mode, bool sparse, bool xp = false) {
         if (rv.KR * rv.S < L) continue;
         const int cpw = 32 / rv.S;
         const int W = (C + cpw - 1) / cpw;
+        if (v == 10 && W != 1) continue;  // 50 window registers per lane: the multi-warp instantiations (512 threads) would spill
         const bool small1 = rv.lreg && W == 1 && rv.S <= 4;  // S = 8: 4 classes x 8 slices, row split would overrun
         const int tm = sparse ? 2 : (small1 ? 0 : 1);
         const int maxt = rv.lreg ? (small1 ? kMaxThreadsSmall1 : kMaxThreadsSmall) : max_threads_big(rv.KR, mode);
@@ -1038,6 +1040,7 @@ static int launch_mode(const DpParams& p, const RegChoice& ch, cudaStream_t st) 
         case 7: return launch_big<MODE, XP, 50, 4>(p, ch, st);
         case 8: return launch_big<MODE, XP, 50, 8>(p, ch, st);
         case 9: return launch_big<MODE, XP, 63, 8>(p, ch, st);
+        case 10: return launch_small<MODE, XP, 50, 2>(p, ch, st);
     }
     set_error("no register-resident DP variant for this shape");
     return -2;
