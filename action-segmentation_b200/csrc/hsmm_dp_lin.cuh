@@ -352,6 +352,10 @@ __device__ __forceinline__ void dp_lin_backward_kernel_body(const DpParams& p, c
     // reasons for handing the video to the log-domain kernel (bflag = 1 + bits): 2 class sum collapsed, 4 flushed-mass
     // bound, 8 length table, 16 NaN
     int why = (valid && (lnmin < -100.0f || fmaxf(maxstep, 0.0f) - lnmin > 110.0f)) ? 8 : 0;
+    if (__any_sync(FULL, why != 0)) {  // known before the first frame: no discarded pass (cf. the forward kernel)
+        if (lane == 0) p.bflag[b] = 9.0f;
+        return;
+    }
     const float ln_first = valid ? p.lenp[(size_t)C + c] * SC : NEG;
 
     float tr[TM == 0 ? CRR : 1], Et[TM == 0 ? CRR : 1];

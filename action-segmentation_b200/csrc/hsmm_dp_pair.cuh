@@ -258,6 +258,13 @@ __device__ __forceinline__ void dp_pair_backward_kernel_body(const DpParams& p, 
         if (maxstep < -1.0e29f) maxstep = 0.0f;
     }
     int why = (valid && (lnmin < -100.0f || fmaxf(maxstep, 0.0f) - lnmin > 110.0f)) ? 8 : 0;
+    {
+        // an unsuitable length table is known before the first frame: flag the video now; leave when neither half has
+        // a video left to process (cf. the forward kernel)
+        const bool half_flag = (__ballot_sync(FULL, why != 0) & q.hmask) != 0u;
+        if (half_flag && c == 0 && have) p.bflag[b] = 9.0f;
+        if (__ballot_sync(FULL, valid && !half_flag) == 0u) return;
+    }
     const float ln_first = valid ? p.lenp[(size_t)C + c] * SC : NEG;
 
     int sidx[SPW];

@@ -165,7 +165,7 @@ SHAPES = [
     # (B, Tmax, C, K, chain, ends)  -- one per compiled DP variant / layout regime
     (9, 60, 23, 20, True, True),     # reg<20,1> trans-reg  (flagship CrossTask shape)
     (9, 60, 9, 20, True, True),      # reg<10,2> trans-reg
-    (7, 150, 11, 100, False, False),  # reg<25,4> trans-smem, 2 warps
+    (7, 150, 11, 100, False, False),  # reg<50,2> trans-reg, one warp (the S6 shape)
     (5, 150, 23, 100, True, True),   # reg<25,4> trans-smem, 3 warps
     (5, 120, 16, 50, False, False),  # reg<25,2> trans-reg
     (4, 120, 64, 50, False, False),  # reg<25,2> trans-smem 4 warps
@@ -457,6 +457,8 @@ LIN_SHAPES = [
     (6, 150, 5, 52, False, False, 3.0),   # lin<13,4>
     (6, 150, 16, 50, False, False, 3.0),  # lin<25,2>
     (6, 120, 3, 30, False, False, 3.0),   # lin<32,1>
+    (6, 150, 11, 100, False, False, 3.0),  # lin<50,2> (the S6 shape: C <= 16, windows of 51..100 frames)
+    (5, 140, 16, 77, True, True, 6.0),    # lin<50,2> sparse
 ]
 
 
