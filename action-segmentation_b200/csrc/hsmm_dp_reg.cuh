@@ -1012,8 +1012,15 @@ static int launch_one(const DpParams& p0, const RegChoice& ch, cudaStream_t st) 
     return check_launch("dp_reg kernel");
 }
 
+constexpr int kMaxThreadsMid = 384;  // backward, W * VPB <= 12 warps: 170 registers instead of 128 (no spills in the frame loop)
 template <int MODE, bool XP, int KR, int S>
 static int launch_small(const DpParams& p, const RegChoice& ch, cudaStream_t st) {
+    if constexpr (MODE == 2 && !XP) {
+        if (ch.W > 1 && ch.W * ch.VPB * 32 <= kMaxThreadsMid && ch.W * ch.VPB * 32 > 256) {
+            return ch.tm == 2 ? launch_one<MODE, XP, KR, S, 2, true, kMaxThreadsMid>(p, ch, st)
+                              : launch_one<MODE, XP, KR, S, 1, true, kMaxThreadsMid>(p, ch, st);
+        }
+    }
     if (ch.tm == 2) {
         return ch.W == 1 ? launch_one<MODE, XP, KR, S, 2, true, kMaxThreadsSmall1>(p, ch, st)
                          : launch_one<MODE, XP, KR, S, 2, true, kMaxThreadsSmall>(p, ch, st);
